@@ -1,0 +1,246 @@
+#!/usr/bin/env python3
+"""Generate golden vectors by EXECUTING THE UNMODIFIED REFERENCE (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  Inputs (weights, rays, latents, randomness) are NOT stored: they are
+re-created bit-identically from seeds by oracle/nrnerf_oracle.py (numpy RandomState / torch
+Generator), so a fixture holds only what the reference computed.
+
+Shims, none of which touch the arithmetic:
+  * empty stand-in modules for imageio / matplotlib (imported at train.py:11,16, unused on the path)
+  * torch.Tensor.get_device returns the tensor's device on CPU (the reference passes the -1 it
+    normally returns as a `device=` argument, e.g. run_nerf_helpers.py:652, train.py:738)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+
+def import_reference():
+    for name in ("imageio", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    _orig = torch.Tensor.get_device
+    torch.Tensor.get_device = lambda t: t.device if not t.is_cuda else _orig(t)
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        import train as ref_train  # noqa
+        import run_nerf_helpers as ref_helpers  # noqa
+    finally:
+        os.chdir(cwd)
+    ref_train.DEBUG = False
+    ref_train.device = torch.device("cpu")
+    return ref_train, ref_helpers
+
+
+def load_nerf(module, p):
+    with torch.no_grad():
+        for i in range(8):
+            module.pts_linears[i].weight.copy_(p["pts_w"][i])
+            module.pts_linears[i].bias.copy_(p["pts_b"][i])
+        module.output_linear.weight.copy_(p["out_w"])
+        module.output_linear.bias.copy_(p["out_b"])
+
+
+def load_bender(module, p):
+    with torch.no_grad():
+        for i in range(5):
+            module.network[i].weight.copy_(p["net_w"][i])
+            if i < 4:
+                module.network[i].bias.copy_(p["net_b"][i])
+        for i in range(3):
+            module.rigidity_network[i].weight.copy_(p["rig_w"][i])
+            module.rigidity_network[i].bias.copy_(p["rig_b"][i])
+
+
+def build_reference_models(rt, rh, O, seed, with_bender=True, density_boost=30.0):
+    embed_fn, input_ch = rh.get_embedder(10, 0)
+    bp = O.make_bender_params(seed + 2) if with_bender else None
+    bender = None
+    if with_bender:
+        bender = rh.ray_bending(input_ch, 32, "simple_neural", embed_fn)
+        load_bender(bender, bp)
+    cp = O.make_nerf_params(seed, 5, density_boost)
+    fp = O.make_nerf_params(seed + 1, 5, density_boost)
+    kw = dict(D=8, W=256, input_ch=input_ch, output_ch=5, skips=[4], input_ch_views=0, use_viewdirs=False,
+              ray_bender=bender, ray_bending_latent_size=32, embeddirs_fn=None, approx_nonrigid_viewdirs=True,
+              time_conditioned_baseline=False)
+    coarse = rh.NeRF(num_ray_samples=64, **kw)
+    fine = rh.NeRF(num_ray_samples=128, **kw)
+    load_nerf(coarse, cp)
+    load_nerf(fine, fp)
+
+    def network_query_fn(inputs, viewdirs, additional_pixel_information, network_fn, detailed_output=False):
+        return rt.run_network(inputs, viewdirs, additional_pixel_information, network_fn, embed_fn=embed_fn,
+                              embeddirs_fn=None, netchunk=65536, detailed_output=detailed_output)
+
+    kwargs = {"network_query_fn": network_query_fn, "perturb": 0.0, "N_importance": 64, "network_fine": fine,
+              "N_samples": 64, "network_fn": coarse, "ray_bender": bender, "use_viewdirs": False,
+              "white_bkgd": False, "raw_noise_std": 0.0, "ndc": False, "lindisp": False}
+    return coarse, fine, bender, kwargs, (cp, fp, bp)
+
+
+def np32(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def grad_summary(tensors, seed=7):
+    rs = np.random.RandomState(seed)
+    out = {}
+    for name, t in tensors:
+        g = t.grad
+        if g is None:
+            continue
+        g = g.detach().reshape(-1)
+        idx = rs.randint(0, g.numel(), size=min(64, g.numel()))
+        out[name + ".norm"] = np.array([float(g.norm())], dtype=np.float64)
+        out[name + ".sum"] = np.array([float(g.double().sum())], dtype=np.float64)
+        out[name + ".idx"] = idx.astype(np.int64)
+        out[name + ".val"] = g[torch.from_numpy(idx)].numpy().astype(np.float32)
+    return out
+
+
+def main():
+    import oracle.nrnerf_oracle as O
+    rt, rh = import_reference()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    outdir = os.path.dirname(os.path.abspath(__file__))
+
+    # ---------------- case A: cfg1 coarse only, bending on, deterministic -----------------------
+    seed, n = 100, 256
+    coarse, fine, bender, kw, _ = build_reference_models(rt, rh, O, seed)
+    rays = O.make_rays(seed, n)
+    kwa = dict(kw); kwa["N_importance"] = 0; kwa["network_fine"] = None
+    # NOTE: the reference raises UnboundLocalError for N_importance == 0 with detailed_output=True
+    # (train.py:969 reads visibility_weights_0, only bound when N_importance > 0), so cfg1 runs plain.
+    with torch.no_grad():
+        rgb, disp, acc, extras = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, near=rays["near"], far=rays["far"],
+                                           additional_pixel_information={"ray_bending_latents": rays["latents"]},
+                                           detailed_output=False, retraw=True, **kwa)
+    np.savez_compressed(os.path.join(outdir, "caseA_coarse_only.npz"), seed=seed, n=n, rgb_map=np32(rgb), disp_map=np32(disp),
+                        acc_map=np32(acc), raw=np32(extras["raw"][:32]), keys=np.array(sorted(extras.keys())))
+
+    # ---------------- case B: coarse + fine, deterministic (test-time render) -------------------
+    seed, n = 200, 256
+    coarse, fine, bender, kw, _ = build_reference_models(rt, rh, O, seed)
+    rays = O.make_rays(seed, n)
+    with torch.no_grad():
+        rgb, disp, acc, extras = rt.render(rays["rays_o"], rays["rays_d"], chunk=100, near=rays["near"], far=rays["far"],
+                                           additional_pixel_information={"ray_bending_latents": rays["latents"]},
+                                           detailed_output=True, retraw=True, **kw)
+    save = dict(seed=seed, n=n, rgb_map=np32(rgb), disp_map=np32(disp), acc_map=np32(acc), rgb0=np32(extras["rgb0"]),
+                disp0=np32(extras["disp0"]), acc0=np32(extras["acc0"]), z_std=np32(extras["z_std"]), raw=np32(extras["raw"][:16]))
+    for k in ("fine_visibility_weights", "fine_opacity_alpha", "visibility_weights", "opacity_alpha", "fine_input_pts",
+              "fine_unmasked_offsets", "fine_masked_offsets", "fine_rigidity_mask", "fine_initial_input_pts",
+              "input_pts", "unmasked_offsets", "masked_offsets", "rigidity_mask", "initial_input_pts"):
+        save[k] = np32(extras[k][:16])
+    save["keys"] = np.array(sorted(extras.keys()))
+    np.savez_compressed(os.path.join(outdir, "caseB_coarse_fine_det.npz"), **save)
+
+    # ---------------- case C: training mode (perturb, sigma noise) + loss + gradients -----------
+    seed, n = 300, 128
+    coarse, fine, bender, kw, _ = build_reference_models(rt, rh, O, seed)
+    rays = O.make_rays(seed, n)
+    rnd = O.make_randomness(seed, n, 64, 64)
+    kwc = dict(kw); kwc["perturb"] = 1.0; kwc["raw_noise_std"] = 1.0
+    latents = rays["latents"].clone().requires_grad_(True)
+    torch.manual_seed(seed)
+    rgb, disp, acc, extras = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, near=rays["near"], far=rays["far"],
+                                       additional_pixel_information={"ray_bending_latents": latents},
+                                       detailed_output=True, retraw=True, **kwc)
+    # the oracle's Generator(seed) must reproduce the global-RNG stream the reference consumed
+    torch.manual_seed(seed)
+    chk = [torch.rand(n, 64), torch.randn(n, 64), torch.rand(n, 64), torch.randn(n, 128)]
+    for a, b in zip(chk, (rnd["t_rand"], rnd["noise_c"], rnd["u"], rnd["noise_f"])):
+        assert torch.equal(a, b), "Generator stream mismatch"
+    target = rays["target"]
+    offsets_w, rigidity_w, sched = 60.0, 5e-4, 0.05
+    loss = rh.img2mse(rgb, target, n) + rh.img2mse(extras["rgb0"], target, n)
+    wts = extras["visibility_weights"].detach().view(-1)
+    ol = torch.mean((wts * torch.pow(torch.norm(extras["unmasked_offsets"].view(-1, 3), dim=-1),
+                                     2.0 - extras["rigidity_mask"].view(-1))).view(n, -1), dim=-1)
+    ol = ol + rigidity_w * torch.mean((wts * extras["rigidity_mask"].view(-1)).view(n, -1), dim=-1)
+    loss = loss + offsets_w * sched * ol
+    loss.mean().backward()
+    named = [("coarse." + k, v) for k, v in coarse.named_parameters()] + \
+            [("fine." + k, v) for k, v in fine.named_parameters()] + \
+            [("bender." + k, v) for k, v in bender.named_parameters()] + [("latents", latents)]
+    save = dict(seed=seed, n=n, rgb_map=np32(rgb), disp_map=np32(disp), acc_map=np32(acc), rgb0=np32(extras["rgb0"]),
+                z_std=np32(extras["z_std"]), loss=np32(loss), raw=np32(extras["raw"][:8]),
+                offsets_w=offsets_w, rigidity_w=rigidity_w, sched=sched, latents_grad=np32(latents.grad))
+    save.update(grad_summary(named))
+    np.savez_compressed(os.path.join(outdir, "caseC_train.npz"), **save)
+
+    # ---------------- case D: test-time editing knobs ------------------------------------------
+    seed, n = 400, 64
+    coarse, fine, bender, kw, _ = build_reference_models(rt, rh, O, seed)
+    rays = O.make_rays(seed, n)
+    bender.rigidity_test_time_cutoff = 0.5
+    bender.test_time_scaling = 1.7
+    coarse.test_time_nonrigid_object_removal_threshold = 0.52
+    fine.test_time_nonrigid_object_removal_threshold = 0.52
+    with torch.no_grad():
+        rgb, disp, acc, extras = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, near=rays["near"], far=rays["far"],
+                                           additional_pixel_information={"ray_bending_latents": rays["latents"]},
+                                           detailed_output=True, retraw=True, **kw)
+    np.savez_compressed(os.path.join(outdir, "caseD_knobs.npz"), seed=seed, n=n, cutoff=0.5, scaling=1.7, removal=0.52,
+                        rgb_map=np32(rgb), disp_map=np32(disp), acc_map=np32(acc), rgb0=np32(extras["rgb0"]),
+                        rigidity_mask=np32(extras["rigidity_mask"][:16]), masked_offsets=np32(extras["masked_offsets"][:16]),
+                        raw=np32(extras["raw"][:8]))
+
+    # ---------------- case E: op-level (sample_pdf, raw2outputs incl. edge cases) ---------------
+    rs = np.random.RandomState(5)
+    nb = 48
+    zc = np.sort(rs.uniform(0.1, 2.0, size=(nb, 64)).astype(np.float32), axis=-1)
+    bins = torch.from_numpy(0.5 * (zc[:, 1:] + zc[:, :-1]))
+    w = rs.uniform(0, 1, size=(nb, 62)).astype(np.float32) ** 4
+    w[0] = 0.0                     # all-zero weights: uniform pdf
+    w[1, :] = 0.0; w[1, 17] = 1.0  # delta: many ties / denom < 1e-5
+    w[2, :30] = 0.0
+    w = torch.from_numpy(w)
+    u_rand = torch.from_numpy(rs.uniform(0, 1, size=(nb, 64)).astype(np.float32))
+    samples_det = rh.sample_pdf(bins, w, 64, det=True)
+    _orig_rand = torch.rand
+    torch.rand = lambda *a, **k: u_rand.clone()   # inject u without touching the reference
+    try:
+        samples_rand = rh.sample_pdf(bins, w, 64, det=False)
+    finally:
+        torch.rand = _orig_rand
+    raw = torch.from_numpy(rs.randn(nb, 64, 5).astype(np.float32) * 3.0)
+    raw[3, :, 3] = -5.0            # zero density everywhere -> acc 0, disp NaN (0/0)
+    raw[4, :, 3] = 50.0            # opaque at the first sample
+    rd = torch.from_numpy(rs.randn(nb, 3).astype(np.float32))
+    z = torch.from_numpy(zc)
+    o = rt.raw2outputs(raw, z, rd, 0.0, False)
+    ow = rt.raw2outputs(raw, z, rd, 0.0, True)
+    np.savez_compressed(os.path.join(outdir, "caseE_ops.npz"), bins=np32(bins), weights=np32(w), u_rand=np32(u_rand),
+                        samples_det=np32(samples_det), samples_rand=np32(samples_rand), raw=np32(raw), z=np32(z), rays_d=np32(rd),
+                        rgb_map=np32(o[0]), disp_map=np32(o[1]), acc_map=np32(o[2]), alpha=np32(o[3]), weights_out=np32(o[4]),
+                        depth_map=np32(o[5]), rgb_map_white=np32(ow[0]))
+
+    # ---------------- case F: canonical rendering (ray_bender = None) --------------------------
+    seed, n = 500, 64
+    coarse, fine, bender, kw, _ = build_reference_models(rt, rh, O, seed, with_bender=False)
+    rays = O.make_rays(seed, n)
+    with torch.no_grad():
+        rgb, disp, acc, extras = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, near=rays["near"], far=rays["far"],
+                                           additional_pixel_information={"ray_bending_latents": rays["latents"]},
+                                           detailed_output=True, retraw=True, **kw)
+    np.savez_compressed(os.path.join(outdir, "caseF_canonical.npz"), seed=seed, n=n, rgb_map=np32(rgb), disp_map=np32(disp),
+                        acc_map=np32(acc), rgb0=np32(extras["rgb0"]), keys=np.array(sorted(extras.keys())))
+    print("golden vectors written to", outdir)
+
+
+if __name__ == "__main__":
+    main()
