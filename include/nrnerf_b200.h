@@ -1,0 +1,124 @@
+/* nrnerf_b200 -- C ABI of the B200-native NR-NeRF render hot path (libnrnerf_b200.so).
+ *
+ * Plain C: raw device pointers, sizes, a cudaStream_t passed as void*.  No torch types, no C++
+ * types, no exceptions.  Every function returns 0 on success or a negative NRN_E_* code; the
+ * message is available from nrn_last_error() (thread-local).  All work is enqueued on the given
+ * stream; nothing synchronises except nrn_device_error().
+ *
+ * The reference (facebookresearch/nonrigid_nerf) has no FFI layer: its boundary for this path is a
+ * set of Python callables.  Each entry point below names the reference function(s) it replaces
+ * (paths relative to the reference checkout); INTEGRATION.md shows the ctypes binding.
+ */
+#ifndef NRNERF_B200_H
+#define NRNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRN_ABI_VERSION 1
+
+#define NRN_OK 0
+#define NRN_E_INVALID (-1)   /* bad argument / unsupported configuration */
+#define NRN_E_CUDA (-2)      /* CUDA runtime error (see nrn_last_error) */
+#define NRN_E_DEVICE (-3)    /* device-side protocol error recorded by a kernel */
+
+int nrn_abi_version(void);
+const char* nrn_last_error(void);
+
+/* Synchronises the current device, reads and clears the device-side error word written by the
+ * fused kernels (0 = ok; non-zero = id of the mbarrier wait that timed out). */
+int nrn_device_error(int* code_out);
+
+/* ---- weight packing -------------------------------------------------------------------------
+ * fp32 nn.Linear tensors in the reference's checkpoint layout ([out][in] row-major) -> fp16 UMMA
+ * operand images.  Replaces nothing in the reference (derived data); sources are
+ * NeRF.pts_linears / output_linear (run_nerf_helpers.py:218-238) and ray_bending.network /
+ * rigidity_network (run_nerf_helpers.py:411-482). */
+size_t nrn_packed_nerf_bytes(void);
+size_t nrn_packed_bender_bytes(void);
+/* w[0..7] = pts_linears.i.weight, w[8] = output_linear.weight; b likewise. input_ch = 63. */
+int nrn_pack_nerf(const float* const* w, const float* const* b, int input_ch, int out_ch, void* packed,
+                  void* stream);
+int nrn_pack_bender(const float* const* net_w /*5*/, const float* const* net_b /*4*/,
+                    const float* const* rig_w /*3*/, const float* const* rig_b /*3*/, int latent_size,
+                    void* packed, void* stream);
+
+/* ---- coarse depth sampling: render_rays, train.py:847-869 ------------------------------------
+ * rays [n][8] = (o, d, near, far); t_rand [n][S] uniform randoms or NULL (perturb == 0). */
+int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_samples, int lindisp,
+                      float* z_vals, void* stream);
+
+/* ---- fused field evaluation: run_network (train.py:57-105) + NeRF.forward
+ * (run_nerf_helpers.py:240-314) + ray_bending.forward (:507-584) + Embedder.embed (:149-150) --- */
+typedef struct NrnFieldArgs {
+  const float* rays;          /* [n_rays][8] (o, d, near, far) */
+  const float* z_vals;        /* [n_rays][n_samples] */
+  const float* points;        /* point mode (NeRF.forward(x), run_nerf_helpers.py:240): rays = z_vals = NULL,
+                                 n_samples = 1, n_rays = number of points; xyz = points[i*points_stride + 0..2] */
+  int64_t points_stride;
+  const float* latents;       /* [n_rays][32], NULL when bender_packed is NULL */
+  int64_t latent_stride;      /* floats between consecutive rays' latents (0 = broadcast one row) */
+  int32_t n_rays;
+  int32_t n_samples;
+  const void* nerf_packed;    /* nrn_pack_nerf output */
+  const void* bender_packed;  /* nrn_pack_bender output or NULL (canonical rendering, ray_bender=(None,)) */
+  int32_t out_ch;             /* 4 or 5 (output_linear rows) */
+  int32_t use_cutoff;  float rigidity_cutoff;   /* ray_bending.rigidity_test_time_cutoff */
+  int32_t use_scaling; float scaling;           /* ray_bending.test_time_scaling */
+  int32_t use_removal; float removal_threshold; /* NeRF.test_time_nonrigid_object_removal_threshold */
+  float* raw;                 /* out [n_rays][n_samples][out_ch] */
+  float* initial_input_pts;   /* out [P][3] or NULL  (details of detailed_output=True) */
+  float* input_pts;           /* out [P][3] or NULL */
+  float* unmasked_offsets;    /* out [P][3] or NULL */
+  float* masked_offsets;      /* out [P][3] or NULL */
+  float* rigidity_mask;       /* out [P]    or NULL */
+  void* stream;
+} NrnFieldArgs;
+int nrn_field_forward(const NrnFieldArgs* args);
+
+/* ---- compositing: raw2outputs (train.py:724-789), optionally fused with sample_pdf
+ * (run_nerf_helpers.py:651-698), the sort of train.py:920 and z_std of train.py:959 ------------ */
+typedef struct NrnCompositeArgs {
+  const float* raw;           /* [n][S][C] */
+  const float* z_vals;        /* [n][S] */
+  const float* rays_d;        /* ray directions, row stride rays_d_stride floats */
+  int32_t rays_d_stride;
+  const float* noise;         /* [n][S] sigma noise already multiplied by raw_noise_std, or NULL */
+  int32_t n_rays, n_samples, channels, white_bkgd;
+  float* rgb_map;             /* out [n][3] */
+  float* disp_map;            /* out [n] */
+  float* acc_map;             /* out [n] */
+  float* depth_map;           /* out [n] or NULL */
+  float* weights;             /* out [n][S] or NULL */
+  float* alpha;               /* out [n][S] or NULL */
+  int32_t n_importance;       /* 0 = composite only */
+  const float* u;             /* [n][n_importance] or NULL (deterministic linspace, perturb == 0) */
+  float* z_vals_out;          /* out [n][S + n_importance] sorted union */
+  float* z_std;               /* out [n] or NULL */
+  void* stream;
+} NrnCompositeArgs;
+int nrn_composite(const NrnCompositeArgs* args);
+
+/* stand-alone sample_pdf (run_nerf_helpers.py:651-698): bins [n][nbins], weights [n][nbins-1] */
+int nrn_sample_pdf(const float* bins, const float* weights, const float* u, int n, int nbins, int n_samples,
+                   float* samples, void* stream);
+
+/* ---- backward of raw2outputs w.r.t. raw (what torch.autograd derives for train.py:724-789) ---- */
+typedef struct NrnCompositeBwdArgs {
+  const float* raw; const float* z_vals; const float* rays_d; int32_t rays_d_stride; const float* noise;
+  int32_t n_rays, n_samples, channels, white_bkgd;
+  const float* d_rgb_map;     /* [n][3] */
+  const float* d_acc_map;     /* [n] or NULL */
+  float* d_raw;               /* out [n][S][C] */
+  void* stream;
+} NrnCompositeBwdArgs;
+int nrn_composite_backward(const NrnCompositeBwdArgs* args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRNERF_B200_H */

@@ -1,0 +1,108 @@
+"""ctypes binding of libnrnerf_b200.so (C ABI declared in include/nrnerf_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+Build it with `python -c "import __graft_entry__ as g; g.build()"` or `make -C nonrigid_nerf_b200/csrc`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnrnerf_b200.so")
+ABI_VERSION = 1
+
+_f32p = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class NrnFieldArgs(C.Structure):
+    _fields_ = [
+        ("rays", _vp), ("z_vals", _vp), ("points", _vp), ("points_stride", C.c_int64),
+        ("latents", _vp), ("latent_stride", C.c_int64),
+        ("n_rays", C.c_int32), ("n_samples", C.c_int32),
+        ("nerf_packed", _vp), ("bender_packed", _vp),
+        ("out_ch", C.c_int32),
+        ("use_cutoff", C.c_int32), ("rigidity_cutoff", C.c_float),
+        ("use_scaling", C.c_int32), ("scaling", C.c_float),
+        ("use_removal", C.c_int32), ("removal_threshold", C.c_float),
+        ("raw", _vp), ("initial_input_pts", _vp), ("input_pts", _vp), ("unmasked_offsets", _vp),
+        ("masked_offsets", _vp), ("rigidity_mask", _vp),
+        ("stream", _vp),
+    ]
+
+
+class NrnCompositeArgs(C.Structure):
+    _fields_ = [
+        ("raw", _vp), ("z_vals", _vp), ("rays_d", _vp), ("rays_d_stride", C.c_int32), ("noise", _vp),
+        ("n_rays", C.c_int32), ("n_samples", C.c_int32), ("channels", C.c_int32), ("white_bkgd", C.c_int32),
+        ("rgb_map", _vp), ("disp_map", _vp), ("acc_map", _vp), ("depth_map", _vp), ("weights", _vp), ("alpha", _vp),
+        ("n_importance", C.c_int32), ("u", _vp), ("z_vals_out", _vp), ("z_std", _vp),
+        ("stream", _vp),
+    ]
+
+
+class NrnCompositeBwdArgs(C.Structure):
+    _fields_ = [
+        ("raw", _vp), ("z_vals", _vp), ("rays_d", _vp), ("rays_d_stride", C.c_int32), ("noise", _vp),
+        ("n_rays", C.c_int32), ("n_samples", C.c_int32), ("channels", C.c_int32), ("white_bkgd", C.c_int32),
+        ("d_rgb_map", _vp), ("d_acc_map", _vp), ("d_raw", _vp),
+        ("stream", _vp),
+    ]
+
+
+# every symbol include/nrnerf_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "nrn_abi_version": (C.c_int, []),
+    "nrn_last_error": (C.c_char_p, []),
+    "nrn_device_error": (C.c_int, [C.POINTER(C.c_int)]),
+    "nrn_packed_nerf_bytes": (C.c_size_t, []),
+    "nrn_packed_bender_bytes": (C.c_size_t, []),
+    "nrn_pack_nerf": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int, _vp, _vp]),
+    "nrn_pack_bender": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.c_int, _vp, _vp]),
+    "nrn_sample_coarse": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "nrn_field_forward": (C.c_int, [C.POINTER(NrnFieldArgs)]),
+    "nrn_composite": (C.c_int, [C.POINTER(NrnCompositeArgs)]),
+    "nrn_sample_pdf": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "nrn_composite_backward": (C.c_int, [C.POINTER(NrnCompositeBwdArgs)]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load the extension once; fail loudly when it is absent or of the wrong ABI version."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"nonrigid_nerf_b200: CUDA extension not found at {LIB_PATH}. There is no CPU/PyTorch fallback; "
+                "build it with `make -C nonrigid_nerf_b200/csrc` (needs nvcc, sm_100a).")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError => symbol missing => broken build
+            fn.restype = res
+            fn.argtypes = args
+        v = lib.nrn_abi_version()
+        if v != ABI_VERSION:
+            raise RuntimeError(f"nonrigid_nerf_b200: ABI version mismatch (library {v}, bindings {ABI_VERSION})")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().nrn_last_error()
+        raise RuntimeError(f"nrnerf_b200 {what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def device_error_check() -> None:
+    """Synchronise and raise if any fused kernel recorded a device-side protocol error."""
+    code = C.c_int(0)
+    check(load().nrn_device_error(C.byref(code)), "device check")

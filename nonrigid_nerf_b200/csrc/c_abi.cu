@@ -1,0 +1,202 @@
+// extern "C" boundary of libnrnerf_b200.so (declarations: include/nrnerf_b200.h).
+// Argument validation, launch, error reporting.  No exceptions cross this file.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "../../include/nrnerf_b200.h"
+#include "nrn_common.cuh"
+#include "pack.cuh"
+#include "ray_ops.cuh"
+
+namespace nrn {
+cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
+}
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(NRN_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  int* err_word = nullptr;
+  int num_sms = 0;
+};
+DeviceState g_dev[kMaxDevices];
+
+int device_state(DeviceState** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kMaxDevices) return fail(NRN_E_INVALID, "device index %d out of range", dev);
+  DeviceState& s = g_dev[dev];
+  if (!s.err_word) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10) return fail(NRN_E_INVALID, "nrnerf_b200 needs an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
+    s.num_sms = prop.multiProcessorCount;
+    e = cudaMalloc(&s.err_word, sizeof(int));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(err word)");
+    e = cudaMemset(s.err_word, 0, sizeof(int));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(err word)");
+  }
+  *out = &s;
+  return NRN_OK;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int nrn_abi_version(void) { return NRN_ABI_VERSION; }
+const char* nrn_last_error(void) { return g_err; }
+
+int nrn_device_error(int* code_out) {
+  DeviceState* ds;
+  int rc = device_state(&ds);
+  if (rc) return rc;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+  int code = 0;
+  e = cudaMemcpy(&code, ds->err_word, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(err word)");
+  if (code) cudaMemset(ds->err_word, 0, sizeof(int));
+  if (code_out) *code_out = code;
+  if (code) return fail(NRN_E_DEVICE, "device-side protocol error: wait id %d timed out", code);
+  return NRN_OK;
+}
+
+size_t nrn_packed_nerf_bytes(void) { return nrn::kNerfPackedBytes; }
+size_t nrn_packed_bender_bytes(void) { return nrn::kBendPackedBytes; }
+
+int nrn_pack_nerf(const float* const* w, const float* const* b, int input_ch, int out_ch, void* packed, void* stream) {
+  if (!w || !b || !packed) return fail(NRN_E_INVALID, "nrn_pack_nerf: null argument");
+  if (input_ch < 1 || input_ch > 63) return fail(NRN_E_INVALID, "nrn_pack_nerf: input_ch=%d unsupported (1..63; multires=10 gives 63)", input_ch);
+  if (out_ch < 4 || out_ch > 16) return fail(NRN_E_INVALID, "nrn_pack_nerf: out_ch=%d unsupported", out_ch);
+  if (!aligned16(packed)) return fail(NRN_E_INVALID, "nrn_pack_nerf: packed buffer must be 16-byte aligned");
+  nrn::NerfSrc src;
+  for (int i = 0; i < 9; ++i) {
+    if (!w[i] || !b[i]) return fail(NRN_E_INVALID, "nrn_pack_nerf: null layer %d", i);
+    src.w[i] = w[i];
+    src.b[i] = b[i];
+  }
+  cudaError_t e = nrn::launch_pack_nerf(src, input_ch, out_ch, packed, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_nerf_kernel");
+}
+
+int nrn_pack_bender(const float* const* net_w, const float* const* net_b, const float* const* rig_w,
+                    const float* const* rig_b, int latent_size, void* packed, void* stream) {
+  if (!net_w || !net_b || !rig_w || !rig_b || !packed) return fail(NRN_E_INVALID, "nrn_pack_bender: null argument");
+  if (latent_size != nrn::kLatent) return fail(NRN_E_INVALID, "nrn_pack_bender: ray_bending_latent_size=%d unsupported (32)", latent_size);
+  if (!aligned16(packed)) return fail(NRN_E_INVALID, "nrn_pack_bender: packed buffer must be 16-byte aligned");
+  nrn::BenderSrc src;
+  for (int i = 0; i < 5; ++i) src.net_w[i] = net_w[i];
+  for (int i = 0; i < 4; ++i) src.net_b[i] = net_b[i];
+  for (int i = 0; i < 3; ++i) { src.rig_w[i] = rig_w[i]; src.rig_b[i] = rig_b[i]; }
+  cudaError_t e = nrn::launch_pack_bender(src, packed, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_bender_kernel");
+}
+
+int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_samples, int lindisp, float* z_vals,
+                      void* stream) {
+  if (n_rays < 0 || n_samples < 1) return fail(NRN_E_INVALID, "nrn_sample_coarse: bad sizes n=%d S=%d", n_rays, n_samples);
+  if (n_rays == 0) return NRN_OK;
+  if (!rays || !z_vals) return fail(NRN_E_INVALID, "nrn_sample_coarse: null argument");
+  cudaError_t e = nrn::launch_sample_coarse(rays, t_rand, n_rays, n_samples, lindisp, z_vals, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "sample_coarse_kernel");
+}
+
+int nrn_field_forward(const NrnFieldArgs* a) {
+  if (!a) return fail(NRN_E_INVALID, "nrn_field_forward: null args");
+  if (a->n_rays < 0 || a->n_samples < 1) return fail(NRN_E_INVALID, "nrn_field_forward: bad sizes n=%d S=%d", a->n_rays, a->n_samples);
+  if (a->n_rays == 0) return NRN_OK;
+  if (!a->nerf_packed || !a->raw) return fail(NRN_E_INVALID, "nrn_field_forward: null argument");
+  if (a->points) {
+    if (a->n_samples != 1 || a->points_stride < 3) return fail(NRN_E_INVALID, "nrn_field_forward: point mode needs n_samples=1, stride>=3");
+  } else if (!a->rays || !a->z_vals) {
+    return fail(NRN_E_INVALID, "nrn_field_forward: null rays / z_vals");
+  }
+  if (a->bender_packed && !a->latents) return fail(NRN_E_INVALID, "nrn_field_forward: bender given without latents");
+  if (a->out_ch < 4 || a->out_ch > 5) return fail(NRN_E_INVALID, "nrn_field_forward: out_ch=%d unsupported (4 or 5)", a->out_ch);
+  if (!aligned16(a->nerf_packed) || (a->bender_packed && !aligned16(a->bender_packed)))
+    return fail(NRN_E_INVALID, "nrn_field_forward: packed weights must be 16-byte aligned");
+  DeviceState* ds;
+  int rc = device_state(&ds);
+  if (rc) return rc;
+  nrn::FieldFwdParams p{};
+  p.rays = a->rays; p.z_vals = a->z_vals; p.pts = a->points; p.pts_stride = a->points_stride; p.latents = a->latents; p.latent_stride = a->latent_stride;
+  p.n_rays = a->n_rays; p.S = a->n_samples;
+  p.P = static_cast<long long>(a->n_rays) * a->n_samples;
+  const long long tiles = (p.P + nrn::kTileM - 1) / nrn::kTileM;
+  if (tiles > 0x7fffffffLL) return fail(NRN_E_INVALID, "nrn_field_forward: too many points");
+  p.n_tiles = static_cast<int>(tiles);
+  const uint8_t* np = static_cast<const uint8_t*>(a->nerf_packed);
+  p.nerf_w = np; p.nerf_bias = reinterpret_cast<const float*>(np + nrn::kNerfWBytes);
+  if (a->bender_packed) {
+    const uint8_t* bp = static_cast<const uint8_t*>(a->bender_packed);
+    p.bend_w = bp; p.bend_bias = reinterpret_cast<const float*>(bp + nrn::kBendWBytes);
+  }
+  p.cutoff = a->rigidity_cutoff; p.use_cutoff = a->use_cutoff;
+  p.scaling = a->scaling; p.use_scaling = a->use_scaling;
+  p.removal = a->removal_threshold; p.use_removal = a->use_removal;
+  p.out_ch = a->out_ch;
+  p.raw = a->raw; p.d_init = a->initial_input_pts; p.d_bent = a->input_pts; p.d_unmasked = a->unmasked_offsets;
+  p.d_masked = a->masked_offsets; p.d_rigid = a->rigidity_mask;
+  p.err = ds->err_word;
+  cudaError_t e = nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "field_fwd_kernel");
+}
+
+int nrn_composite(const NrnCompositeArgs* a) {
+  if (!a) return fail(NRN_E_INVALID, "nrn_composite: null args");
+  if (a->n_rays < 0 || a->n_samples < 1 || a->channels < 4) return fail(NRN_E_INVALID, "nrn_composite: bad sizes");
+  if (a->n_rays == 0) return NRN_OK;
+  if (!a->raw || !a->z_vals || !a->rays_d || !a->rgb_map || !a->disp_map || !a->acc_map) return fail(NRN_E_INVALID, "nrn_composite: null argument");
+  if (a->n_importance < 0) return fail(NRN_E_INVALID, "nrn_composite: n_importance < 0");
+  if (a->n_importance > 0 && (!a->z_vals_out || a->n_samples < 3)) return fail(NRN_E_INVALID, "nrn_composite: resampling needs z_vals_out and >= 3 samples");
+  if (4 * a->n_samples + a->n_importance > 12000) return fail(NRN_E_INVALID, "nrn_composite: too many samples per ray");
+  nrn::CompositeParams p{};
+  p.raw = a->raw; p.z = a->z_vals; p.rays_d = a->rays_d; p.rays_d_stride = a->rays_d_stride; p.noise = a->noise;
+  p.n = a->n_rays; p.S = a->n_samples; p.C = a->channels; p.white_bkgd = a->white_bkgd;
+  p.rgb = a->rgb_map; p.disp = a->disp_map; p.acc = a->acc_map; p.depth = a->depth_map; p.weights = a->weights; p.alpha = a->alpha;
+  p.n_imp = a->n_importance; p.u = a->u; p.z_out = a->z_vals_out; p.z_std = a->z_std;
+  cudaError_t e = nrn::launch_composite(p, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "composite_kernel");
+}
+
+int nrn_sample_pdf(const float* bins, const float* weights, const float* u, int n, int nbins, int n_samples, float* samples,
+                   void* stream) {
+  if (n < 0 || nbins < 2 || n_samples < 1 || nbins > 4000) return fail(NRN_E_INVALID, "nrn_sample_pdf: bad sizes");
+  if (n == 0) return NRN_OK;
+  if (!bins || !weights || !samples) return fail(NRN_E_INVALID, "nrn_sample_pdf: null argument");
+  cudaError_t e = nrn::launch_sample_pdf(bins, weights, u, n, nbins, n_samples, samples, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "sample_pdf_kernel");
+}
+
+int nrn_composite_backward(const NrnCompositeBwdArgs* a) {
+  if (!a) return fail(NRN_E_INVALID, "nrn_composite_backward: null args");
+  if (a->n_rays < 0 || a->n_samples < 1 || a->channels < 4 || a->n_samples > 12000) return fail(NRN_E_INVALID, "nrn_composite_backward: bad sizes");
+  if (a->n_rays == 0) return NRN_OK;
+  if (!a->raw || !a->z_vals || !a->rays_d || !a->d_rgb_map || !a->d_raw) return fail(NRN_E_INVALID, "nrn_composite_backward: null argument");
+  nrn::CompositeBwdParams p{};
+  p.raw = a->raw; p.z = a->z_vals; p.rays_d = a->rays_d; p.rays_d_stride = a->rays_d_stride; p.noise = a->noise;
+  p.n = a->n_rays; p.S = a->n_samples; p.C = a->channels; p.white_bkgd = a->white_bkgd;
+  p.d_rgb = a->d_rgb_map; p.d_acc = a->d_acc_map; p.d_raw = a->d_raw;
+  cudaError_t e = nrn::launch_composite_bwd(p, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "composite_bwd_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+"""Host-side mirror of the reference's train.py hot-path entry points.
+
+render / batchify_rays / render_rays / run_network / batchify / raw2outputs keep the reference's
+names, argument meaning, return structure and error behaviour (train.py:27-137, :326-416,
+:724-980), but run on the fused sm_100a kernels.  torch.nn.DataParallel (train.py:290-323) is
+replaced by ray sharding over torch.distributed/NCCL (parallel.py).
+
+Randomness is drawn host-side from the global torch generator in the reference's order
+(t_rand -> sigma noise coarse -> u -> sigma noise fine; train.py:861, :753, run_nerf_helpers.py:666)
+and passed to the kernels, so a seeded run consumes the same stream as the reference.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import autograd as _ag
+from . import ops
+from .run_nerf_helpers import NeRF, img2mse, mse2psnr  # noqa: F401  (same star-import surface)
+
+DEBUG = False  # reference: train.py:24 (NaN/Inf scan of every output when True)
+
+
+# ---- run_network / batchify (train.py:27-105) ----------------------------------------------------
+def batchify(fn, chunk, detailed_output=False):
+    """Kept for API compatibility: the fused kernel needs no activation chunking, so `chunk` only
+    bounds the size of one launch."""
+    if chunk is None:
+        return fn
+
+    def ret(inputs):
+        outs = [fn(inputs[i:i + chunk], detailed_output=detailed_output) for i in range(0, inputs.shape[0], chunk)]
+        if detailed_output:
+            outputs = torch.cat([o[0] for o in outs], 0)
+            details = {k: torch.cat([o[1][k] for o in outs], 0) for k in outs[0][1]}
+            return outputs, details
+        return torch.cat(outs, 0)
+
+    return ret
+
+
+def run_network(inputs, viewdirs, additional_pixel_information, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64,
+                detailed_output=False):
+    """Prepares inputs and applies network `fn` (train.py:57-105).  inputs: [N_rays, N_samples, 3]."""
+    if viewdirs is not None:
+        raise RuntimeError("nonrigid_nerf_b200: use_viewdirs=True is not implemented yet (SURVEY.md 8f row f1)")
+    n, s = inputs.shape[0], inputs.shape[1]
+    latents = additional_pixel_information["ray_bending_latents"]
+    pts = inputs.reshape(-1, 3)
+    lat = latents[:, None].expand(n, s, latents.shape[-1]).reshape(n * s, latents.shape[-1])
+    raw, details = _ag.field_points(fn, pts, lat, detailed_output)
+    outputs = raw.reshape(n, s, -1)
+    if detailed_output:
+        return outputs, {k: v.reshape(n, s, -1) for k, v in details.items()}
+    return outputs
+
+
+# ---- raw2outputs (train.py:724-789) ---------------------------------------------------------------
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+    """Returns rgb_map, disp_map, acc_map, opacity_alpha, visibility_weights, depth_map."""
+    if pytest:
+        raise RuntimeError("nonrigid_nerf_b200: the pytest= numpy-random hook is not supported")
+    noise = None
+    if raw_noise_std > 0.0:
+        noise = torch.randn(raw[..., 3].shape, device=raw.device) * raw_noise_std
+    o = _ag.composite(raw, z_vals, rays_d, noise, white_bkgd)
+    return o["rgb_map"], o["disp_map"], o["acc_map"], o["alpha"], o["weights"], o["depth_map"]
+
+
+# ---- render_rays (train.py:792-980) ---------------------------------------------------------------
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.0,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0.0,
+                additional_pixel_information=None, detailed_output=False, verbose=False, pytest=False, **dummy_kwargs):
+    """Volumetric rendering of a ray batch [N, 8] = (o, d, near, far).  `network_query_fn` is accepted
+    for signature compatibility; the field is evaluated by the fused kernel on `network_fn` /
+    `network_fine` (which carry their ray bender as `.ray_bender[0]`)."""
+    if pytest:
+        raise RuntimeError("nonrigid_nerf_b200: the pytest= numpy-random hook is not supported")
+    if ray_batch.shape[-1] > 8:
+        raise RuntimeError("nonrigid_nerf_b200: use_viewdirs=True is not implemented yet (SURVEY.md 8f row f1)")
+    if not isinstance(network_fn, NeRF) or (network_fine is not None and not isinstance(network_fine, NeRF)):
+        raise RuntimeError("nonrigid_nerf_b200: render_rays needs nonrigid_nerf_b200.run_nerf_helpers.NeRF modules")
+    n = ray_batch.shape[0]
+    dev = ray_batch.device
+    rays = ray_batch if (ray_batch.dtype == torch.float32 and ray_batch.is_contiguous()) else ray_batch.float().contiguous()
+    rays_d = rays[:, 3:6]
+    latents = None
+    if network_fn.ray_bender[0] is not None:
+        latents = additional_pixel_information["ray_bending_latents"]
+
+    # coarse depths (train.py:847-869); t_rand drawn first, like the reference
+    t_rand = torch.rand(n, N_samples, device=dev) if perturb > 0.0 else None
+    z_vals = ops.sample_coarse(rays, N_samples, t_rand, lindisp)
+    raw, details = _ag.field(network_fn, rays, z_vals, latents, detailed_output)
+    noise = torch.randn(n, N_samples, device=dev) * raw_noise_std if raw_noise_std > 0.0 else None
+
+    if N_importance > 0:
+        u = torch.rand(n, N_importance, device=dev) if perturb > 0.0 else None   # det=(perturb == 0), train.py:915
+        c0 = _ag.composite(raw, z_vals, rays_d, noise, white_bkgd, N_importance, u)
+        z_fine = c0["z_vals_out"]   # sorted union, detached (train.py:918-920)
+        run_fn = network_fn if network_fine is None else network_fine
+        raw, fine_details = _ag.field(run_fn, rays, z_fine, latents, detailed_output)
+        noise_f = torch.randn(n, N_samples + N_importance, device=dev) * raw_noise_std if raw_noise_std > 0.0 else None
+        c1 = _ag.composite(raw, z_fine, rays_d, noise_f, white_bkgd)
+    else:
+        c0 = None
+        c1 = _ag.composite(raw, z_vals, rays_d, noise, white_bkgd)
+
+    ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"]}
+    if retraw:
+        ret["raw"] = raw
+    if N_importance > 0:
+        ret["rgb0"], ret["disp0"], ret["acc0"] = c0["rgb_map"], c0["disp_map"], c0["acc_map"]
+        ret["z_std"] = c0["z_std"]
+        if detailed_output:
+            ret["fine_visibility_weights"] = c1["weights"]
+            ret["fine_opacity_alpha"] = c1["alpha"]
+            for key, val in fine_details.items():
+                ret["fine_" + str(key)] = val
+    if detailed_output:
+        first = c0 if c0 is not None else c1   # (the reference raises UnboundLocalError here when N_importance == 0)
+        ret["visibility_weights"] = first["weights"]
+        ret["opacity_alpha"] = first["alpha"]
+        for key, val in details.items():
+            ret[key] = val
+    if DEBUG:
+        for k in ret:
+            if torch.isnan(ret[k]).any() or torch.isinf(ret[k]).any():
+                print(f"! [Numerical Error] {k} contains nan or inf.", flush=True)
+    return ret
+
+
+# ---- batchify_rays / render (train.py:108-137, :326-416) --------------------------------------------
+def batchify_rays(rays_flat, additional_pixel_information, chunk=1024 * 32, detailed_output=False, **kwargs):
+    """Render rays in chunks (`chunk` only bounds the per-launch working set; results do not depend on it)."""
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        info = {"ray_bending_latents": additional_pixel_information["ray_bending_latents"][i:i + chunk, :]}
+        ret = render_rays(rays_flat[i:i + chunk], additional_pixel_information=info, detailed_output=detailed_output, **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
+
+
+def render(rays_o, rays_d, chunk=1024 * 32, ndc=True, near=0.0, far=1.0, use_viewdirs=False, c2w_staticcam=None,
+           additional_pixel_information=None, detailed_output=False, **kwargs):
+    """Render rays.  Returns [rgb_map, disp_map, acc_map, extras] (train.py:326-416)."""
+    if use_viewdirs:
+        raise RuntimeError("nonrigid_nerf_b200: use_viewdirs=True is not implemented yet (SURVEY.md 8f row f1)")
+    sh = rays_d.shape
+    if ndc:
+        raise RuntimeError("not implemented. change H, W, focal to use ray_params instead")  # train.py:384-386
+    if not rays_o.is_cuda:
+        raise RuntimeError("nonrigid_nerf_b200: rays must be CUDA tensors (there is no CPU path)")
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near_t = near * torch.ones_like(rays_d[..., :1])
+    far_t = far * torch.ones_like(rays_d[..., :1])
+    rays = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+    all_ret = batchify_rays(rays, additional_pixel_information, chunk=chunk, detailed_output=detailed_output, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ["rgb_map", "disp_map", "acc_map"]
+    ret_list = [all_ret[k] for k in k_extract]
+    ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
+    return ret_list + [ret_dict]
