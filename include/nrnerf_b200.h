@@ -76,6 +76,7 @@ typedef struct NrnFieldArgs {
   float* unmasked_offsets;    /* out [P][3] or NULL */
   float* masked_offsets;      /* out [P][3] or NULL */
   float* rigidity_mask;       /* out [P]    or NULL */
+  void* stash;                /* training only: activation stash of nrn_stash_bytes() bytes, else NULL */
   void* stream;
 } NrnFieldArgs;
 int nrn_field_forward(const NrnFieldArgs* args);
@@ -117,6 +118,37 @@ typedef struct NrnCompositeBwdArgs {
   void* stream;
 } NrnCompositeBwdArgs;
 int nrn_composite_backward(const NrnCompositeBwdArgs* args);
+
+/* ---- backward of the fused field (what torch.autograd derives for NeRF.forward +
+ * ray_bending.forward, run_nerf_helpers.py:240-314 / :507-584):
+ * DGRAD chain + WGRAD + deterministic split reduction.  Needs the stash written by
+ * nrn_field_forward (ray mode) and, with a bender, that call's unmasked_offsets / rigidity_mask. */
+size_t nrn_stash_bytes(int n_rays, int n_samples);
+size_t nrn_grad_stash_bytes(int n_rays, int n_samples);
+size_t nrn_wgrad_scratch_bytes(void);
+int nrn_nerf_grad_floats(int out_ch);   /* flat order: W0 b0 W1 b1 ... W7 b7 Wout bout (reference shapes) */
+int nrn_bender_grad_floats(void);       /* flat order: network.0.w .0.b .1.w .1.b .2.w .2.b .3.w .3.b .4.w,
+                                           rigidity_network.0.w .0.b .1.w .1.b .2.w .2.b */
+typedef struct NrnFieldBwdArgs {
+  int32_t n_rays, n_samples, out_ch;
+  const float* d_raw;             /* [n_rays][n_samples][out_ch] upstream gradient */
+  const void* stash;              /* from the forward call */
+  void* grad_stash;               /* workspace, nrn_grad_stash_bytes() */
+  float* wgrad_scratch;           /* workspace, nrn_wgrad_scratch_bytes() */
+  const void* nerf_packed;
+  const void* bender_packed;      /* or NULL */
+  const float* unmasked_offsets;  /* [P][3] forward output (bender only) */
+  const float* rigidity_mask;     /* [P]    forward output (bender only) */
+  const float* d_unmasked_offsets;/* [P][3] upstream gradient (offsets regulariser) or NULL */
+  const float* d_rigidity_mask;   /* [P]    upstream gradient (rigidity regulariser) or NULL */
+  int32_t use_cutoff;  float rigidity_cutoff;
+  int32_t use_scaling; float scaling;
+  float* nerf_grad;               /* out, nrn_nerf_grad_floats(out_ch) floats, overwritten */
+  float* bender_grad;             /* out, nrn_bender_grad_floats() floats, overwritten (or NULL) */
+  float* d_latents;               /* out [n_rays][32], overwritten (or NULL without bender) */
+  void* stream;
+} NrnFieldBwdArgs;
+int nrn_field_backward(const NrnFieldBwdArgs* args);
 
 #ifdef __cplusplus
 }

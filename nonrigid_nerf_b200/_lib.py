@@ -29,6 +29,20 @@ class NrnFieldArgs(C.Structure):
         ("use_removal", C.c_int32), ("removal_threshold", C.c_float),
         ("raw", _vp), ("initial_input_pts", _vp), ("input_pts", _vp), ("unmasked_offsets", _vp),
         ("masked_offsets", _vp), ("rigidity_mask", _vp),
+        ("stash", _vp),
+        ("stream", _vp),
+    ]
+
+
+class NrnFieldBwdArgs(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int32), ("n_samples", C.c_int32), ("out_ch", C.c_int32),
+        ("d_raw", _vp), ("stash", _vp), ("grad_stash", _vp), ("wgrad_scratch", _vp),
+        ("nerf_packed", _vp), ("bender_packed", _vp),
+        ("unmasked_offsets", _vp), ("rigidity_mask", _vp), ("d_unmasked_offsets", _vp), ("d_rigidity_mask", _vp),
+        ("use_cutoff", C.c_int32), ("rigidity_cutoff", C.c_float),
+        ("use_scaling", C.c_int32), ("scaling", C.c_float),
+        ("nerf_grad", _vp), ("bender_grad", _vp), ("d_latents", _vp),
         ("stream", _vp),
     ]
 
@@ -66,6 +80,12 @@ SYMBOLS = {
     "nrn_composite": (C.c_int, [C.POINTER(NrnCompositeArgs)]),
     "nrn_sample_pdf": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "nrn_composite_backward": (C.c_int, [C.POINTER(NrnCompositeBwdArgs)]),
+    "nrn_stash_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nrn_grad_stash_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nrn_wgrad_scratch_bytes": (C.c_size_t, []),
+    "nrn_nerf_grad_floats": (C.c_int, [C.c_int]),
+    "nrn_bender_grad_floats": (C.c_int, []),
+    "nrn_field_backward": (C.c_int, [C.POINTER(NrnFieldBwdArgs)]),
 }
 
 _lib = None

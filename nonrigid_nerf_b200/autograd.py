@@ -2,14 +2,23 @@
 
 PyTorch owns every tensor (weights stay nn.Parameters with the reference's names); the extension
 keeps a derived packed fp16 copy (ops.pack_*), rebuilt when a parameter's version counter changes.
+Gradients come back from the DGRAD/WGRAD kernels as flat fp32 buffers laid out in the reference's
+parameter shapes and are handed to autograd as views, so the reference's Adam, its two-pass
+test-latent backward (train.py:1595-1608) and the PyTorch-side regularisers keep working unchanged.
+
+Gradient flow implemented: rgb_map / acc_map -> raw -> both MLPs -> positional
+encoding -> bent point -> bender weights and per-ray latents; plus upstream gradients on the coarse
+`unmasked_offsets` / `rigidity_mask` details (offsets / rigidity regularisers, train.py:219-242).
+z_vals, ray origins/directions and the importance samples carry no gradient (train.py:918).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, Optional, Tuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 def _knobs(net):
@@ -20,10 +29,184 @@ def _knobs(net):
     return cutoff, scaling, removal
 
 
-def field_rays(net, rays: torch.Tensor, z_vals: torch.Tensor, latents: Optional[torch.Tensor],
-               want_details: bool) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-    """Fused field evaluation for rays x samples (inference path; the differentiable path is
-    autograd_train.FieldTrainFn)."""
+def _flat_params(net, bender):
+    """Parameters in the flat order of the WGRAD output buffers (csrc/wgrad.cu)."""
+    ws, bs = ops.nerf_param_list(net)
+    nerf = []
+    for w, b in zip(ws, bs):
+        nerf += [w, b]
+    bend = []
+    if bender is not None:
+        net_w, net_b, rig_w, rig_b = ops.bender_param_list(bender)
+        for i in range(4):
+            bend += [net_w[i], net_b[i]]
+        bend.append(net_w[4])
+        for i in range(3):
+            bend += [rig_w[i], rig_b[i]]
+    return nerf, bend
+
+
+def _split_flat(flat: torch.Tensor, like):
+    out, o = [], 0
+    for p in like:
+        n = p.numel()
+        out.append(flat[o:o + n].view_as(p))
+        o += n
+    assert o == flat.numel(), (o, flat.numel())
+    return out
+
+
+class _FieldTrainFn(torch.autograd.Function):
+    """raw, unmasked_offsets, rigidity_mask (differentiable) + point details (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, net, rays, z_vals, latents, n_nerf, *params):
+        bender = net.ray_bender[0]
+        cutoff, scaling, removal = _knobs(net)
+        if removal is not None:
+            raise RuntimeError("nonrigid_nerf_b200: test_time_nonrigid_object_removal_threshold is a test-time knob; "
+                               "it is not differentiable")
+        nerf_pack = ops.pack_nerf(net)
+        bender_pack = ops.pack_bender(bender) if bender is not None else None
+        out_ch = net.output_linear.weight.shape[0]
+        n, s = z_vals.shape
+        lib = _lib.load()
+        stash = torch.empty(lib.nrn_stash_bytes(n, s), dtype=torch.uint8, device=z_vals.device)
+        raw, det = ops.field_forward(rays, z_vals, latents, nerf_pack, bender_pack, out_ch, cutoff, scaling, None, True, stash)
+        ctx.net, ctx.n_nerf = net, n_nerf
+        ctx.shape = (n, s, out_ch)
+        ctx.knobs = (cutoff, scaling)
+        ctx.packs = (nerf_pack, bender_pack)
+        ctx.stash = stash
+        ctx.params = params
+        ctx.set_materialize_grads(False)
+        if bender is not None:
+            ctx.save_for_backward(det["unmasked_offsets"], det["rigidity_mask"])
+            outs = (raw, det["unmasked_offsets"], det["rigidity_mask"], det["initial_input_pts"], det["input_pts"],
+                    det["masked_offsets"])
+            ctx.mark_non_differentiable(*outs[3:])
+        else:
+            outs = (raw, det["initial_input_pts"], det["input_pts"])
+            ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_raw, *rest):
+        net = ctx.net
+        bender = net.ray_bender[0]
+        n, s, out_ch = ctx.shape
+        nerf_pack, bender_pack = ctx.packs
+        cutoff, scaling = ctx.knobs
+        dev = ctx.stash.device
+        lib = _lib.load()
+        d_un = d_rig = None
+        if bender is not None:
+            d_un, d_rig = rest[0], rest[1]
+        if d_raw is None:
+            d_raw = torch.zeros(n, s, out_ch, dtype=torch.float32, device=dev)
+        a = _lib.NrnFieldBwdArgs()
+        a.n_rays, a.n_samples, a.out_ch = n, s, out_ch
+        d_raw = d_raw.contiguous().float()
+        a.d_raw = d_raw.data_ptr()
+        a.stash = ctx.stash.data_ptr()
+        gstash = torch.empty(lib.nrn_grad_stash_bytes(n, s), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(lib.nrn_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
+        a.grad_stash, a.wgrad_scratch = gstash.data_ptr(), scratch.data_ptr()
+        a.nerf_packed = nerf_pack.data_ptr()
+        nerf_grad = torch.empty(lib.nrn_nerf_grad_floats(out_ch), dtype=torch.float32, device=dev)
+        a.nerf_grad = nerf_grad.data_ptr()
+        bend_grad = d_lat = None
+        keep = [d_raw]
+        if bender is not None:
+            un, rig = ctx.saved_tensors
+            a.bender_packed = bender_pack.data_ptr()
+            a.unmasked_offsets, a.rigidity_mask = un.data_ptr(), rig.data_ptr()
+            if d_un is not None:
+                d_un = d_un.contiguous().float()
+                a.d_unmasked_offsets = d_un.data_ptr()
+                keep.append(d_un)
+            if d_rig is not None:
+                d_rig = d_rig.contiguous().float()
+                a.d_rigidity_mask = d_rig.data_ptr()
+                keep.append(d_rig)
+            if cutoff is not None:
+                a.use_cutoff, a.rigidity_cutoff = 1, float(cutoff)
+            if scaling is not None:
+                a.use_scaling, a.scaling = 1, float(scaling)
+            bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
+            d_lat = torch.empty(n, ops.LATENT, dtype=torch.float32, device=dev)
+            a.bender_grad, a.d_latents = bend_grad.data_ptr(), d_lat.data_ptr()
+        a.stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrn_field_backward(C.byref(a)), "field_backward")
+        ctx.stash = None
+        nerf_p, bend_p = ctx.params[:ctx.n_nerf], ctx.params[ctx.n_nerf:]
+        grads = _split_flat(nerf_grad, nerf_p)
+        if bender is not None:
+            grads += _split_flat(bend_grad, bend_p)
+        grads = [g if p.requires_grad else None for g, p in zip(grads, ctx.params)]
+        return (None, None, None, d_lat, None, *grads)
+
+
+class _CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, n_importance, u):
+        o = ops.composite(raw, z_vals, rays_d, noise, white_bkgd, n_importance, u, True)
+        ctx.save_for_backward(raw, z_vals, rays_d, noise if noise is not None else raw.new_empty(0))
+        ctx.has_noise = noise is not None
+        ctx.white = bool(white_bkgd)
+        ctx.set_materialize_grads(False)
+        outs = [o["rgb_map"], o["acc_map"], o["disp_map"], o["depth_map"], o["weights"], o["alpha"]]
+        if n_importance > 0:
+            outs += [o["z_vals_out"], o["z_std"]]
+        ctx.mark_non_differentiable(*outs[2:])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_acc, *unsupported):
+        raw, z_vals, rays_d, noise = ctx.saved_tensors
+        if d_rgb is None and d_acc is None:
+            return None, None, None, None, None, None, None
+        if d_rgb is None:
+            d_rgb = torch.zeros(raw.shape[0], 3, dtype=torch.float32, device=raw.device)
+        d_raw = ops.composite_backward(raw, z_vals, rays_d, noise if ctx.has_noise else None, ctx.white, d_rgb, d_acc)
+        return d_raw, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# entry points used by train.py / run_nerf_helpers.py
+# ---------------------------------------------------------------------------------------------
+def _needs_grad(net, latents) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    bender = net.ray_bender[0]
+    if latents is not None and latents.requires_grad:
+        return True
+    if any(p.requires_grad for p in net.parameters()):
+        return True
+    return bender is not None and any(p.requires_grad for p in bender.parameters())
+
+
+def field(net, rays: torch.Tensor, z_vals: torch.Tensor, latents: Optional[torch.Tensor],
+          want_details: bool) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """Fused field evaluation for rays x samples; differentiable when autograd is recording."""
+    bender = net.ray_bender[0]
+    if not _needs_grad(net, latents):
+        return field_rays(net, rays, z_vals, latents, want_details)
+    nerf_p, bend_p = _flat_params(net, bender)
+    outs = _FieldTrainFn.apply(net, rays, z_vals, latents, len(nerf_p), *nerf_p, *bend_p)
+    if bender is not None:
+        raw, un, rig, init, bent, masked = outs
+        details = {"initial_input_pts": init, "unmasked_offsets": un, "rigidity_mask": rig, "masked_offsets": masked,
+                   "input_pts": bent}
+    else:
+        raw, init, bent = outs
+        details = {"initial_input_pts": init, "input_pts": bent}
+    return raw, (details if want_details else {})
+
+
+def field_rays(net, rays, z_vals, latents, want_details):
+    """Inference path (no stash)."""
     bender = net.ray_bender[0]
     cutoff, scaling, removal = _knobs(net)
     nerf_pack = ops.pack_nerf(net)
@@ -32,11 +215,23 @@ def field_rays(net, rays: torch.Tensor, z_vals: torch.Tensor, latents: Optional[
     return ops.field_forward(rays, z_vals, latents, nerf_pack, bender_pack, out_ch, cutoff, scaling, removal, want_details)
 
 
-def field_points(net, pts: torch.Tensor, latents: Optional[torch.Tensor], want_details: bool):
-    """NeRF.forward(x) semantics: one xyz (+ latent) per row."""
+def field_points(net, pts, latents, want_details):
+    """NeRF.forward(x) semantics: one xyz (+ latent) per row.  Inference only."""
+    if _needs_grad(net, latents):
+        raise RuntimeError("nonrigid_nerf_b200: the point-wise NeRF.forward / run_network entry is inference-only; "
+                           "differentiable rendering goes through render() / render_rays()")
     bender = net.ray_bender[0]
     cutoff, scaling, removal = _knobs(net)
     nerf_pack = ops.pack_nerf(net)
     bender_pack = ops.pack_bender(bender) if bender is not None else None
     out_ch = net.output_linear.weight.shape[0]
     return ops.field_forward_points(pts, latents, nerf_pack, bender_pack, out_ch, cutoff, scaling, removal, want_details)
+
+
+def composite(raw, z_vals, rays_d, noise=None, white_bkgd=False, n_importance=0, u=None) -> Dict[str, torch.Tensor]:
+    """raw2outputs (+ hierarchical resampling); differentiable w.r.t. raw through rgb_map / acc_map."""
+    if torch.is_grad_enabled() and raw.requires_grad:
+        outs = _CompositeFn.apply(raw, z_vals, rays_d, noise, white_bkgd, n_importance, u)
+        keys = ["rgb_map", "acc_map", "disp_map", "depth_map", "weights", "alpha"] + (["z_vals_out", "z_std"] if n_importance > 0 else [])
+        return dict(zip(keys, outs))
+    return ops.composite(raw, z_vals, rays_d, noise, white_bkgd, n_importance, u, True)

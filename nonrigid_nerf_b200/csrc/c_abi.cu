@@ -7,9 +7,11 @@
 #include "nrn_common.cuh"
 #include "pack.cuh"
 #include "ray_ops.cuh"
+#include "wgrad.cuh"
 
 namespace nrn {
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
+cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 }
 
 namespace {
@@ -29,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 constexpr int kMaxDevices = 64;
 struct DeviceState {
-  int* err_word = nullptr;
+  int* err_word = nullptr;   // [0] error word, [1] loss-scale source (float) of the running backward
   int num_sms = 0;
 };
 DeviceState g_dev[kMaxDevices];
@@ -46,9 +48,9 @@ int device_state(DeviceState** out) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
     if (prop.major != 10) return fail(NRN_E_INVALID, "nrnerf_b200 needs an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
     s.num_sms = prop.multiProcessorCount;
-    e = cudaMalloc(&s.err_word, sizeof(int));
+    e = cudaMalloc(&s.err_word, 4 * sizeof(int));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(err word)");
-    e = cudaMemset(s.err_word, 0, sizeof(int));
+    e = cudaMemset(s.err_word, 0, 4 * sizeof(int));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(err word)");
   }
   *out = &s;
@@ -94,7 +96,9 @@ int nrn_pack_nerf(const float* const* w, const float* const* b, int input_ch, in
     src.b[i] = b[i];
   }
   cudaError_t e = nrn::launch_pack_nerf(src, input_ch, out_ch, packed, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_nerf_kernel");
+  if (e != cudaSuccess) return cuda_fail(e, "pack_nerf_kernel");
+  e = nrn::launch_pack_nerf_t(src, input_ch, out_ch, static_cast<uint8_t*>(packed) + nrn::kNerfTOffset, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_nerf_t_kernel");
 }
 
 int nrn_pack_bender(const float* const* net_w, const float* const* net_b, const float* const* rig_w,
@@ -107,7 +111,9 @@ int nrn_pack_bender(const float* const* net_w, const float* const* net_b, const 
   for (int i = 0; i < 4; ++i) src.net_b[i] = net_b[i];
   for (int i = 0; i < 3; ++i) { src.rig_w[i] = rig_w[i]; src.rig_b[i] = rig_b[i]; }
   cudaError_t e = nrn::launch_pack_bender(src, packed, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_bender_kernel");
+  if (e != cudaSuccess) return cuda_fail(e, "pack_bender_kernel");
+  e = nrn::launch_pack_bender_t(src, static_cast<uint8_t*>(packed) + nrn::kBendTOffset, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_bender_t_kernel");
 }
 
 int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_samples, int lindisp, float* z_vals,
@@ -155,6 +161,8 @@ int nrn_field_forward(const NrnFieldArgs* a) {
   p.out_ch = a->out_ch;
   p.raw = a->raw; p.d_init = a->initial_input_pts; p.d_bent = a->input_pts; p.d_unmasked = a->unmasked_offsets;
   p.d_masked = a->masked_offsets; p.d_rigid = a->rigidity_mask;
+  p.stash = static_cast<uint8_t*>(a->stash);
+  if (a->stash && a->points) return fail(NRN_E_INVALID, "nrn_field_forward: the training stash needs ray mode");
   p.err = ds->err_word;
   cudaError_t e = nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream));
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "field_fwd_kernel");
@@ -197,6 +205,66 @@ int nrn_composite_backward(const NrnCompositeBwdArgs* a) {
   p.d_rgb = a->d_rgb_map; p.d_acc = a->d_acc_map; p.d_raw = a->d_raw;
   cudaError_t e = nrn::launch_composite_bwd(p, static_cast<cudaStream_t>(a->stream));
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "composite_bwd_kernel");
+}
+
+static long long even_tiles(int n_rays, int n_samples) {
+  const long long P = static_cast<long long>(n_rays) * n_samples;
+  const long long tiles = (P + nrn::kTileM - 1) / nrn::kTileM;
+  return (tiles + 1) & ~1LL;   // the kernels work on tile pairs
+}
+size_t nrn_stash_bytes(int n_rays, int n_samples) { return static_cast<size_t>(even_tiles(n_rays, n_samples)) * nrn::kStashTileBytes; }
+size_t nrn_grad_stash_bytes(int n_rays, int n_samples) { return static_cast<size_t>(even_tiles(n_rays, n_samples)) * nrn::kGradTileBytes; }
+size_t nrn_wgrad_scratch_bytes(void) { return static_cast<size_t>(nrn::kWgMaxCtas) * nrn::kWgScratchFloats * sizeof(float); }
+int nrn_nerf_grad_floats(int out_ch) { return 256 * 63 + 256 + 6 * (65536 + 256) + 256 * 319 + 256 + out_ch * 257; }
+int nrn_bender_grad_floats(void) { return 16193; }
+
+int nrn_field_backward(const NrnFieldBwdArgs* a) {
+  if (!a) return fail(NRN_E_INVALID, "nrn_field_backward: null args");
+  if (a->n_rays < 0 || a->n_samples < 1) return fail(NRN_E_INVALID, "nrn_field_backward: bad sizes");
+  if (a->out_ch < 4 || a->out_ch > 5) return fail(NRN_E_INVALID, "nrn_field_backward: out_ch=%d unsupported", a->out_ch);
+  if (!a->nerf_packed || !a->nerf_grad) return fail(NRN_E_INVALID, "nrn_field_backward: null argument");
+  const bool bend = a->bender_packed != nullptr;
+  if (bend && (!a->unmasked_offsets || !a->rigidity_mask || !a->bender_grad || !a->d_latents))
+    return fail(NRN_E_INVALID, "nrn_field_backward: bender needs unmasked_offsets, rigidity_mask, bender_grad, d_latents");
+  DeviceState* ds;
+  int rc = device_state(&ds);
+  if (rc) return rc;
+  if (ds->num_sms + 16 > nrn::kWgMaxCtas) return fail(NRN_E_INVALID, "nrn_field_backward: %d SMs exceed the scratch layout", ds->num_sms);
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  const int nerf_n = nrn_nerf_grad_floats(a->out_ch);
+  const int bend_n = bend ? nrn_bender_grad_floats() : 0;
+  cudaError_t e;
+  if (bend) {
+    e = cudaMemsetAsync(a->d_latents, 0, sizeof(float) * static_cast<size_t>(a->n_rays) * nrn::kLatent, st);
+    if (e != cudaSuccess) return cuda_fail(e, "memset d_latents");
+  }
+  if (a->n_rays == 0) {
+    e = cudaMemsetAsync(a->nerf_grad, 0, sizeof(float) * nerf_n, st);
+    if (e == cudaSuccess && bend) e = cudaMemsetAsync(a->bender_grad, 0, sizeof(float) * bend_n, st);
+    return e == cudaSuccess ? NRN_OK : cuda_fail(e, "memset grads");
+  }
+  if (!a->d_raw || !a->stash || !a->grad_stash || !a->wgrad_scratch) return fail(NRN_E_INVALID, "nrn_field_backward: null argument");
+  float* amax = reinterpret_cast<float*>(ds->err_word + 1);
+  nrn::FieldBwdParams p{};
+  p.P = static_cast<long long>(a->n_rays) * a->n_samples;
+  p.n_tiles = static_cast<int>((p.P + nrn::kTileM - 1) / nrn::kTileM);
+  p.S = a->n_samples; p.n_rays = a->n_rays; p.out_ch = a->out_ch;
+  p.d_raw = a->d_raw; p.amax = amax;
+  p.stash = static_cast<const uint8_t*>(a->stash); p.gstash = static_cast<uint8_t*>(a->grad_stash);
+  p.nerf_wT = static_cast<const uint8_t*>(a->nerf_packed) + nrn::kNerfTOffset;
+  if (bend) p.bend_wT = static_cast<const uint8_t*>(a->bender_packed) + nrn::kBendTOffset;
+  p.unmasked = a->unmasked_offsets; p.rigidity = a->rigidity_mask;
+  p.d_unmasked_up = a->d_unmasked_offsets; p.d_rigid_up = a->d_rigidity_mask;
+  p.cutoff = a->rigidity_cutoff; p.use_cutoff = a->use_cutoff; p.scaling = a->scaling; p.use_scaling = a->use_scaling;
+  p.d_latents = a->d_latents; p.err = ds->err_word;
+  e = nrn::launch_absmax(a->d_raw, p.P * a->out_ch, amax, st);
+  if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
+  e = nrn::launch_field_bwd(p, bend, ds->num_sms, st);
+  if (e != cudaSuccess) return cuda_fail(e, "field_bwd_kernel");
+  nrn::WgradParams w{};
+  w.stash = p.stash; w.gstash = p.gstash; w.scratch = a->wgrad_scratch; w.amax = amax; w.n_tiles = p.n_tiles; w.err = ds->err_word;
+  e = nrn::launch_wgrad(w, bend, ds->num_sms, a->nerf_grad, nerf_n, a->bender_grad, bend_n, a->out_ch, st);
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "wgrad_kernel");
 }
 
 }  // extern "C"

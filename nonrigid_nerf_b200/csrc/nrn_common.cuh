@@ -32,7 +32,7 @@ constexpr int kNerfL5Bytes = 40 * 256 * 16;
 constexpr int kNerfHeadBytes = 32 * 16 * 16;
 constexpr int kNerfWBytes = kNerfL0Bytes + 6 * kNerfLBytes + kNerfL5Bytes + kNerfHeadBytes;  // 991,232
 constexpr int kNerfBiasFloats = 8 * 256 + 16;
-constexpr int kNerfPackedBytes = kNerfWBytes + kNerfBiasFloats * 4;
+constexpr int kNerfTOffset = kNerfWBytes + kNerfBiasFloats * 4;   // transposed images (DGRAD) follow the biases
 
 // Packed ray-bender weights (fp16): offset MLP and rigidity MLP fused block-diagonally.
 //   B0: N=96 K=48  rows 0-63 offset L0 (cols: xyz_hi 0-2, xyz_lo 3-5, latent 6-37), rows 64-95 rigidity L0
@@ -48,8 +48,70 @@ constexpr int kBendB3Bytes = 8 * 64 * 16;
 constexpr int kBendB4Bytes = 8 * 16 * 16;
 constexpr int kBendWBytes = kBendB0Bytes + kBendB1Bytes + kBendB2Bytes + kBendB3Bytes + kBendB4Bytes;  // 53,248
 constexpr int kBendBiasFloats = 96 + 96 + 80 + 64;
-constexpr int kBendPackedBytes = kBendWBytes + kBendBiasFloats * 4;
+constexpr int kBendTOffset = kBendWBytes + kBendBiasFloats * 4;
 constexpr int kLatent = 32;
+
+// ------------------------------------------------------------------------------------------
+// Training stash (forward -> backward), per 128-point tile, fp16 chunk-major tile images:
+//   E  (positional encoding of the bent point, 64 cols; the pad column 63 holds 1.0 so that the
+//       WGRAD of L0 / L5 yields the bias gradient in that column)
+//   H1..H8 (post-ReLU activations), bender input and hidden activations.
+// Gradient stash (DGRAD -> WGRAD), same format: d_raw, dY7..dY0, bender dY's.
+// ------------------------------------------------------------------------------------------
+constexpr int kStE = 0;
+constexpr int kStH = kStE + kEBytes;                       // H_l at kStH + (l-1)*kHBytes, l = 1..8
+constexpr int kStBin = kStH + 8 * kHBytes;                 // bender input, 6 chunks
+constexpr int kStHb1 = kStBin + 6 * kChunkBytes;           // 12 chunks
+constexpr int kStHb2 = kStHb1 + 12 * kChunkBytes;          // 12 chunks
+constexpr int kStHb3 = kStHb2 + 12 * kChunkBytes;          // 8 chunks
+constexpr int kStHb4 = kStHb3 + 8 * kChunkBytes;           // 8 chunks
+constexpr int kStashTileBytes = kStHb4 + 8 * kChunkBytes;  // 634,880
+
+constexpr int kGsRaw = 0;                                  // d_raw, 2 chunks (16 cols)
+constexpr int kGsY = kGsRaw + 2 * kChunkBytes;             // dY_l at kGsY + l*kHBytes, l = 0..7
+constexpr int kGsYb4 = kGsY + 8 * kHBytes;                 // 2 chunks (d unmasked offsets)
+constexpr int kGsYb3 = kGsYb4 + 2 * kChunkBytes;           // 8 chunks
+constexpr int kGsYb2 = kGsYb3 + 8 * kChunkBytes;           // 10 chunks (64 + rigidity pre-activation + pad)
+constexpr int kGsYb1 = kGsYb2 + 10 * kChunkBytes;          // 12 chunks
+constexpr int kGsYb0 = kGsYb1 + 12 * kChunkBytes;          // 12 chunks
+constexpr int kGradTileBytes = kGsYb0 + 12 * kChunkBytes;  // 618,496
+
+// ------------------------------------------------------------------------------------------
+// Transposed weight images for DGRAD (dX = dY . W: B operand = W^T, rows = input features,
+// K = output features), fp16, in the order field_bwd.cu streams them (pack_t.cu):
+//   head^T [2 chunks][256][8] | L7^T L6^T [32][256][8] | L5e^T [32][64][8] | L5h^T L4^T..L1^T | L0^T [32][64][8]
+//   bender: B4^T [2][64][8] | B3^T [8][64][8] | B2^T [10][96][8] | B1^T [12][96][8] | B0^T [12][48][8]
+// ------------------------------------------------------------------------------------------
+constexpr int kNerfTHeadBytes = 2 * 256 * 16;
+constexpr int kNerfTEBytes = 32 * 64 * 16;
+constexpr int kNerfTWBytes = kNerfTHeadBytes + 7 * kNerfLBytes + 2 * kNerfTEBytes;
+constexpr int kBendTB4Bytes = 2 * 64 * 16;
+constexpr int kBendTB3Bytes = 8 * 64 * 16;
+constexpr int kBendTB2Bytes = 10 * 96 * 16;
+constexpr int kBendTB1Bytes = 12 * 96 * 16;
+constexpr int kBendTB0Bytes = 12 * 48 * 16;
+constexpr int kBendTWBytes = kBendTB4Bytes + kBendTB3Bytes + kBendTB2Bytes + kBendTB1Bytes + kBendTB0Bytes;
+constexpr int kNerfPackedBytes = kNerfTOffset + kNerfTWBytes;
+constexpr int kBendPackedBytes = kBendTOffset + kBendTWBytes;
+
+struct FieldBwdParams {
+  long long P;
+  int n_tiles, S, n_rays, out_ch;
+  const float* d_raw;          // [P][out_ch] upstream gradient of the raw field output
+  const float* amax;           // device scalar: max |d_raw| (loss-scale source) or null (scale 1)
+  const uint8_t* stash;        // forward stash   [n_tiles even][kStashTileBytes]
+  uint8_t* gstash;             // gradient stash  [n_tiles even][kGradTileBytes]
+  const uint8_t* nerf_wT;
+  const uint8_t* bend_wT;
+  const float* unmasked;       // [P][3] forward details (bender only)
+  const float* rigidity;       // [P]
+  const float* d_unmasked_up;  // [P][3] upstream gradient from the offsets regulariser, or null
+  const float* d_rigid_up;     // [P]    upstream gradient from the rigidity regulariser, or null
+  float cutoff, scaling;
+  int use_cutoff, use_scaling;
+  float* d_latents;            // [n_rays][32] fp32, zero-initialised, accumulated with atomics
+  int* err;
+};
 
 // ------------------------------------------------------------------------------------------
 // Kernel parameter blocks
@@ -77,6 +139,7 @@ struct FieldFwdParams {
   float* d_unmasked;      // [P][3] or null
   float* d_masked;        // [P][3] or null
   float* d_rigid;         // [P]    or null
+  uint8_t* stash;         // training stash [n_tiles rounded up to even][kStashTileBytes] or null
   int* err;               // device error word (0 = ok)
 };
 

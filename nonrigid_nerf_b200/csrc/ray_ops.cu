@@ -168,7 +168,8 @@ composite_kernel(const CompositeParams p) {
     p.rgb[ray * 3 + 0] = acc_r + bg; p.rgb[ray * 3 + 1] = acc_g + bg; p.rgb[ray * 3 + 2] = acc_b + bg;
     p.acc[ray] = acc_w;
     if (p.depth) p.depth[ray] = acc_d;
-    p.disp[ray] = 1.0f / fmaxf(1e-10f, acc_d / acc_w);                 // :781-784 (NaN when acc == 0)
+    const float q = acc_d / acc_w;                                     // :781-784; 0/0 = NaN when acc == 0 and
+    p.disp[ray] = 1.0f / (q != q ? q : fmaxf(1e-10f, q));              // torch.max propagates it (fmaxf would not)
   }
   if (p.n_imp <= 0) return;
   __syncwarp();

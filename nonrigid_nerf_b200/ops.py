@@ -119,7 +119,7 @@ def sample_coarse(rays: torch.Tensor, n_samples: int, t_rand: Optional[torch.Ten
     return z
 
 
-def _field(rays, z_vals, points, latents, nerf_pack, bender_pack, out_ch, cutoff, scaling, removal, want_details):
+def _field(rays, z_vals, points, latents, nerf_pack, bender_pack, out_ch, cutoff, scaling, removal, want_details, stash=None):
     a = _lib.NrnFieldArgs()
     keep = []
     if points is None:
@@ -175,6 +175,8 @@ def _field(rays, z_vals, points, latents, nerf_pack, bender_pack, out_ch, cutoff
             a.unmasked_offsets = details["unmasked_offsets"].data_ptr()
             a.masked_offsets = details["masked_offsets"].data_ptr()
             a.rigidity_mask = details["rigidity_mask"].data_ptr()
+    if stash is not None:
+        a.stash = stash.data_ptr()
     a.stream = torch.cuda.current_stream().cuda_stream
     with torch.cuda.device(dev):
         _lib.check(_lib.load().nrn_field_forward(C.byref(a)), "field_forward")
@@ -184,9 +186,10 @@ def _field(rays, z_vals, points, latents, nerf_pack, bender_pack, out_ch, cutoff
 def field_forward(rays: torch.Tensor, z_vals: torch.Tensor, latents: Optional[torch.Tensor], nerf_pack: torch.Tensor,
                   bender_pack: Optional[torch.Tensor], out_ch: int, cutoff: Optional[float] = None,
                   scaling: Optional[float] = None, removal: Optional[float] = None,
-                  want_details: bool = False) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
-    """One fused pass over rays x samples: raw [N, S, out_ch] (+ the reference's per-point `details`)."""
-    return _field(rays, z_vals, None, latents, nerf_pack, bender_pack, out_ch, cutoff, scaling, removal, want_details)
+                  want_details: bool = False, stash: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """One fused pass over rays x samples: raw [N, S, out_ch] (+ the reference's per-point `details`).
+    `stash` (uint8, nrn_stash_bytes) switches the kernel to training mode (activations kept for backward)."""
+    return _field(rays, z_vals, None, latents, nerf_pack, bender_pack, out_ch, cutoff, scaling, removal, want_details, stash)
 
 
 def field_forward_points(points: torch.Tensor, latents: Optional[torch.Tensor], nerf_pack: torch.Tensor,

@@ -72,7 +72,10 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                 additional_pixel_information=None, detailed_output=False, verbose=False, pytest=False, **dummy_kwargs):
     """Volumetric rendering of a ray batch [N, 8] = (o, d, near, far).  `network_query_fn` is accepted
     for signature compatibility; the field is evaluated by the fused kernel on `network_fn` /
-    `network_fine` (which carry their ray bender as `.ray_bender[0]`)."""
+    `network_fine` (which carry their ray bender as `.ray_bender[0]`).
+    Extra keyword `randomness` (dict with t_rand, noise_c, u, noise_f; unit-variance noise) replaces
+    the internal draws -- the supported way to reproduce a run exactly (the reference's `pytest` hook
+    re-seeds numpy instead, train.py:863-867)."""
     if pytest:
         raise RuntimeError("nonrigid_nerf_b200: the pytest= numpy-random hook is not supported")
     if ray_batch.shape[-1] > 8:
@@ -87,19 +90,26 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     if network_fn.ray_bender[0] is not None:
         latents = additional_pixel_information["ray_bending_latents"]
 
+    rnd = dummy_kwargs.get("randomness", None)
+
+    def draw(key, fn, *shape):
+        if rnd is not None:
+            return rnd[key].to(dev)
+        return fn(*shape, device=dev)
+
     # coarse depths (train.py:847-869); t_rand drawn first, like the reference
-    t_rand = torch.rand(n, N_samples, device=dev) if perturb > 0.0 else None
+    t_rand = draw("t_rand", torch.rand, n, N_samples) if perturb > 0.0 else None
     z_vals = ops.sample_coarse(rays, N_samples, t_rand, lindisp)
     raw, details = _ag.field(network_fn, rays, z_vals, latents, detailed_output)
-    noise = torch.randn(n, N_samples, device=dev) * raw_noise_std if raw_noise_std > 0.0 else None
+    noise = draw("noise_c", torch.randn, n, N_samples) * raw_noise_std if raw_noise_std > 0.0 else None
 
     if N_importance > 0:
-        u = torch.rand(n, N_importance, device=dev) if perturb > 0.0 else None   # det=(perturb == 0), train.py:915
+        u = draw("u", torch.rand, n, N_importance) if perturb > 0.0 else None   # det=(perturb == 0), train.py:915
         c0 = _ag.composite(raw, z_vals, rays_d, noise, white_bkgd, N_importance, u)
         z_fine = c0["z_vals_out"]   # sorted union, detached (train.py:918-920)
         run_fn = network_fn if network_fine is None else network_fine
         raw, fine_details = _ag.field(run_fn, rays, z_fine, latents, detailed_output)
-        noise_f = torch.randn(n, N_samples + N_importance, device=dev) * raw_noise_std if raw_noise_std > 0.0 else None
+        noise_f = draw("noise_f", torch.randn, n, N_samples + N_importance) * raw_noise_std if raw_noise_std > 0.0 else None
         c1 = _ag.composite(raw, z_fine, rays_d, noise_f, white_bkgd)
     else:
         c0 = None

@@ -1,0 +1,182 @@
+"""GPU parity of the public entry points (render / render_rays, forward and backward) against the
+oracle and against the golden vectors the executed reference produced.
+
+Tolerances (fp16 tensor-core operands, fp32 accumulation, vs the fp32 reference):
+  per-pixel RGB L-inf <= 5e-3, acc <= 5e-3, PSNR(new vs reference image) >= 50 dB
+  gradients: relative L2 error per parameter tensor <= 3e-2 (5e-2 for the tiny bender tensors)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.nrnerf_oracle as O
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda:0"
+
+
+def _render(coarse, fine, bender, r, n_imp=64, perturb=0.0, noise=0.0, rnd=None, detailed=True, chunk=32768, **extra):
+    from nonrigid_nerf_b200 import train as T
+    kw = dict(network_query_fn=None, perturb=perturb, N_importance=n_imp, network_fine=fine if n_imp > 0 else None,
+              N_samples=64, network_fn=coarse, ray_bender=bender, use_viewdirs=False, white_bkgd=False,
+              raw_noise_std=noise, ndc=False, lindisp=False)
+    kw.update(extra)
+    if rnd is not None:
+        kw["randomness"] = rnd
+    lat = r["latents"].to(DEV) if not isinstance(r["latents"], torch.Tensor) or not r["latents"].is_cuda else r["latents"]
+    return T.render(r["rays_o"].to(DEV), r["rays_d"].to(DEV), chunk=chunk, near=r["near"], far=r["far"],
+                    additional_pixel_information={"ray_bending_latents": lat}, detailed_output=detailed, retraw=True, **kw)
+
+
+def _psnr(a, b):
+    mse = float(((a - b) ** 2).mean())
+    return 99.0 if mse == 0 else -10.0 * np.log10(mse)
+
+
+def test_render_matches_golden_caseB_and_keys():
+    from nonrigid_nerf_b200 import _lib
+    g = np.load(os.path.join(GOLD, "caseB_coarse_fine_det.npz"))
+    seed, n = int(g["seed"]), int(g["n"])
+    coarse, fine, bender, _ = helpers.build_models(O, seed, DEV)
+    r = O.make_rays(seed, n)
+    with torch.no_grad():
+        rgb, disp, acc, extras = _render(coarse, fine, bender, r, chunk=100)   # ragged chunks like the golden run
+    _lib.device_error_check()
+    assert set(str(k) for k in g["keys"]) == set(extras.keys())
+    for name, ours in (("rgb_map", rgb), ("rgb0", extras["rgb0"]), ("acc_map", acc), ("acc0", extras["acc0"])):
+        d = np.abs(ours.cpu().numpy() - g[name]).max()
+        print(f"{name}: L-inf {d:.3e}")
+        assert d <= 5e-3, (name, d)
+    assert _psnr(rgb.cpu().numpy(), g["rgb_map"]) >= 50.0
+    np.testing.assert_allclose(extras["z_std"].cpu().numpy(), g["z_std"], atol=2e-3)
+    np.testing.assert_allclose(disp.cpu().numpy(), g["disp_map"], rtol=2e-2, atol=1e-3)
+    np.testing.assert_allclose(extras["fine_rigidity_mask"][:16].cpu().numpy(), g["fine_rigidity_mask"], atol=1e-4)
+    np.testing.assert_allclose(extras["unmasked_offsets"][:16].cpu().numpy(), g["unmasked_offsets"], atol=2e-5)
+    assert extras["raw"].shape == (n, 128, 5) and extras["fine_input_pts"].shape == (n, 128, 3)
+
+
+def test_render_golden_caseA_coarse_only_and_caseF_canonical():
+    g = np.load(os.path.join(GOLD, "caseA_coarse_only.npz"))
+    seed, n = int(g["seed"]), int(g["n"])
+    coarse, fine, bender, _ = helpers.build_models(O, seed, DEV)
+    r = O.make_rays(seed, n)
+    with torch.no_grad():
+        rgb, disp, acc, extras = _render(coarse, None, bender, r, n_imp=0, detailed=False)
+    assert set(str(k) for k in g["keys"]) == set(extras.keys())
+    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= 5e-3
+    assert np.abs(acc.cpu().numpy() - g["acc_map"]).max() <= 5e-3
+    g = np.load(os.path.join(GOLD, "caseF_canonical.npz"))
+    seed, n = int(g["seed"]), int(g["n"])
+    coarse, fine, _, _ = helpers.build_models(O, seed, DEV, with_bender=False)
+    r = O.make_rays(seed, n)
+    with torch.no_grad():
+        rgb, disp, acc, extras = _render(coarse, fine, None, r)
+    assert set(str(k) for k in g["keys"]) == set(extras.keys())
+    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= 5e-3
+    assert np.abs(extras["rgb0"].cpu().numpy() - g["rgb0"]).max() <= 5e-3
+
+
+def test_render_golden_caseD_test_time_knobs():
+    g = np.load(os.path.join(GOLD, "caseD_knobs.npz"))
+    seed, n = int(g["seed"]), int(g["n"])
+    coarse, fine, bender, _ = helpers.build_models(O, seed, DEV)
+    bender.rigidity_test_time_cutoff = float(g["cutoff"])
+    bender.test_time_scaling = float(g["scaling"])
+    coarse.test_time_nonrigid_object_removal_threshold = float(g["removal"])
+    fine.test_time_nonrigid_object_removal_threshold = float(g["removal"])
+    r = O.make_rays(seed, n)
+    with torch.no_grad():
+        rgb, disp, acc, extras = _render(coarse, fine, bender, r)
+    # the cut-off is a hard threshold on a value computed at different precision: allow a few flipped points
+    rm = extras["rigidity_mask"][:16].cpu().numpy()
+    bad = np.abs(rm - g["rigidity_mask"]) > 1e-4
+    assert bad.mean() < 0.01, bad.mean()
+    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= 2e-2
+    assert _psnr(rgb.cpu().numpy(), g["rgb_map"]) >= 45.0
+
+
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_training_step_forward_and_gradients_match_oracle_and_golden():
+    from nonrigid_nerf_b200 import _lib
+    g = np.load(os.path.join(GOLD, "caseC_train.npz"))
+    seed, n = int(g["seed"]), int(g["n"])
+    coarse, fine, bender, (cp, fp, bp) = helpers.build_models(O, seed, DEV)
+    r = O.make_rays(seed, n)
+    rnd = O.make_randomness(seed, n, 64, 64)
+    lat = r["latents"].clone().to(DEV).requires_grad_(True)
+    rr = dict(r); rr["latents"] = lat
+    rgb, disp, acc, extras = _render(coarse, fine, bender, rr, perturb=1.0, noise=1.0, rnd=rnd)
+    ret = {"rgb_map": rgb, "rgb0": extras["rgb0"], "visibility_weights": extras["visibility_weights"],
+           "unmasked_offsets": extras["unmasked_offsets"], "rigidity_mask": extras["rigidity_mask"]}
+    loss = O.training_loss(ret, r["target"].to(DEV), float(g["offsets_w"]), float(g["rigidity_w"]), float(g["sched"]))
+    loss.mean().backward()
+    _lib.device_error_check()
+    # forward vs the executed reference
+    for name, ours in (("rgb_map", rgb), ("rgb0", extras["rgb0"])):
+        d = np.abs(ours.detach().cpu().numpy() - g[name]).max()
+        print(f"{name}: L-inf {d:.3e}")
+        assert d <= 5e-3, (name, d)
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["loss"], atol=3e-3)
+    # gradients vs the oracle's autograd on identical inputs
+    cpo, fpo, bpo = O.clone_params(cp, True), O.clone_params(fp, True), O.clone_params(bp, True)
+    lat_o = r["latents"].clone().requires_grad_(True)
+    ret_o = O.render_rays(cpo, fpo, bpo, r["rays_o"], r["rays_d"], r["near"], r["far"], lat_o, 64, 64, perturb=True,
+                          raw_noise_std=1.0, rnd=rnd)
+    O.training_loss(ret_o, r["target"], float(g["offsets_w"]), float(g["rigidity_w"]), float(g["sched"])).mean().backward()
+    worst = 0.0
+    for net, po in ((coarse, cpo), (fine, fpo)):
+        for i in range(8):
+            for ours, ref in ((net.pts_linears[i].weight.grad, po["pts_w"][i].grad), (net.pts_linears[i].bias.grad, po["pts_b"][i].grad)):
+                e = _rel(ours.cpu(), ref); worst = max(worst, e)
+                assert e <= 3e-2, (i, e)
+        e = _rel(net.output_linear.weight.grad.cpu(), po["out_w"].grad); worst = max(worst, e)
+        assert e <= 3e-2, ("out_w", e)
+        e = _rel(net.output_linear.bias.grad.cpu(), po["out_b"].grad)
+        assert e <= 3e-2, ("out_b", e)
+        assert net.views_linears[0].weight.grad is None   # dead weight keeps grad=None
+    for i in range(5):
+        e = _rel(bender.network[i].weight.grad.cpu(), bpo["net_w"][i].grad); worst = max(worst, e)
+        assert e <= 5e-2, ("net_w", i, e)
+        if i < 4:
+            e = _rel(bender.network[i].bias.grad.cpu(), bpo["net_b"][i].grad)
+            assert e <= 5e-2, ("net_b", i, e)
+    for i in range(3):
+        e = _rel(bender.rigidity_network[i].weight.grad.cpu(), bpo["rig_w"][i].grad); worst = max(worst, e)
+        assert e <= 5e-2, ("rig_w", i, e)
+        e = _rel(bender.rigidity_network[i].bias.grad.cpu(), bpo["rig_b"][i].grad)
+        assert e <= 5e-2, ("rig_b", i, e)
+    e = _rel(lat.grad.cpu(), lat_o.grad)
+    assert e <= 3e-2, ("latents", e)
+    print(f"worst relative gradient error {worst:.3e}; latents {e:.3e}")
+    # and against the gradient samples stored from the executed reference
+    for nm, t in (("coarse.pts_linears.3.weight", coarse.pts_linears[3].weight), ("fine.pts_linears.5.weight", fine.pts_linears[5].weight),
+                  ("bender.network.0.weight", bender.network[0].weight)):
+        idx = torch.from_numpy(g[nm + ".idx"])
+        ours = t.grad.reshape(-1).cpu()[idx].numpy()
+        ref = g[nm + ".val"]
+        assert np.linalg.norm(ours - ref) <= 5e-2 * np.linalg.norm(ref) + 1e-9, nm
+
+
+def test_gradients_without_bender_and_ragged_batch():
+    from nonrigid_nerf_b200 import _lib
+    seed, n = 901, 77
+    coarse, fine, _, (cp, fp, _) = helpers.build_models(O, seed, DEV, with_bender=False)
+    r = O.make_rays(seed, n)
+    rgb, disp, acc, extras = _render(coarse, fine, None, r, detailed=False)
+    tgt = r["target"].to(DEV)
+    (((rgb - tgt) ** 2).mean() + ((extras["rgb0"] - tgt) ** 2).mean()).backward()
+    _lib.device_error_check()
+    cpo, fpo = O.clone_params(cp, True), O.clone_params(fp, True)
+    ret = O.render_rays(cpo, fpo, None, r["rays_o"], r["rays_d"], r["near"], r["far"], r["latents"], 64, 64)
+    (((ret["rgb_map"] - r["target"]) ** 2).mean() + ((ret["rgb0"] - r["target"]) ** 2).mean()).backward()
+    for net, po in ((coarse, cpo), (fine, fpo)):
+        for i in (0, 4, 5, 7):
+            e = _rel(net.pts_linears[i].weight.grad.cpu(), po["pts_w"][i].grad)
+            assert e <= 3e-2, (i, e)
