@@ -150,6 +150,13 @@ typedef struct NrnFieldBwdArgs {
 } NrnFieldBwdArgs;
 int nrn_field_backward(const NrnFieldBwdArgs* args);
 
+/* ---- optional per-kernel timing (measurement aid for bench.py) ---------------------------------
+ * While enabled, every launch of the kernel kinds below is bracketed by CUDA events recorded on the
+ * launch stream.  kinds: 0 field forward, 1 field DGRAD, 2 WGRAD (+reduce), 3 composite(+resample),
+ * 4 composite backward.  nrn_timing_read synchronises the recorded events and returns per-kind sums. */
+int nrn_timing_enable(int on);
+int nrn_timing_read(double* ms_sum, int* counts, int n_kinds);
+
 #ifdef __cplusplus
 }
 #endif

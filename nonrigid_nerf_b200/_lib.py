@@ -86,7 +86,24 @@ SYMBOLS = {
     "nrn_nerf_grad_floats": (C.c_int, [C.c_int]),
     "nrn_bender_grad_floats": (C.c_int, []),
     "nrn_field_backward": (C.c_int, [C.POINTER(NrnFieldBwdArgs)]),
+    "nrn_timing_enable": (C.c_int, [C.c_int]),
+    "nrn_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }
+
+KERNEL_KINDS = ("field_fwd", "field_dgrad", "wgrad", "composite", "composite_bwd")
+
+
+def timing_enable(on: bool) -> None:
+    check(load().nrn_timing_enable(1 if on else 0), "timing_enable")
+
+
+def timing_read():
+    """{kind: (total_ms, launches)} for the launches recorded since timing_enable(True)."""
+    n = len(KERNEL_KINDS)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int * n)()
+    check(load().nrn_timing_read(ms, cnt, n), "timing_read")
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(KERNEL_KINDS)}
 
 _lib = None
 _lock = threading.Lock()

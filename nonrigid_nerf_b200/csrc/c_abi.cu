@@ -59,6 +59,30 @@ int device_state(DeviceState** out) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- optional per-kernel timing: CUDA events recorded on the launch stream around each kernel ----
+struct TimedLaunch {
+  cudaEvent_t a, b;
+  int kind;
+};
+bool g_timing = false;
+TimedLaunch g_timed[4096];
+int g_timed_n = 0;
+struct ScopedTimer {
+  int idx = -1;
+  cudaStream_t st;
+  ScopedTimer(int kind, cudaStream_t s) : st(s) {
+    if (!g_timing || g_timed_n >= 4096) return;
+    TimedLaunch& t = g_timed[g_timed_n];
+    if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+    t.kind = kind;
+    idx = g_timed_n++;
+    cudaEventRecord(t.a, st);
+  }
+  ~ScopedTimer() {
+    if (idx >= 0) cudaEventRecord(g_timed[idx].b, st);
+  }
+};
+
 }  // namespace
 
 extern "C" {
@@ -164,7 +188,7 @@ int nrn_field_forward(const NrnFieldArgs* a) {
   p.stash = static_cast<uint8_t*>(a->stash);
   if (a->stash && a->points) return fail(NRN_E_INVALID, "nrn_field_forward: the training stash needs ray mode");
   p.err = ds->err_word;
-  cudaError_t e = nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream));
+  cudaError_t e; { ScopedTimer tm(0, static_cast<cudaStream_t>(a->stream)); e = nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream)); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "field_fwd_kernel");
 }
 
@@ -181,7 +205,7 @@ int nrn_composite(const NrnCompositeArgs* a) {
   p.n = a->n_rays; p.S = a->n_samples; p.C = a->channels; p.white_bkgd = a->white_bkgd;
   p.rgb = a->rgb_map; p.disp = a->disp_map; p.acc = a->acc_map; p.depth = a->depth_map; p.weights = a->weights; p.alpha = a->alpha;
   p.n_imp = a->n_importance; p.u = a->u; p.z_out = a->z_vals_out; p.z_std = a->z_std;
-  cudaError_t e = nrn::launch_composite(p, static_cast<cudaStream_t>(a->stream));
+  cudaError_t e; { ScopedTimer tm(3, static_cast<cudaStream_t>(a->stream)); e = nrn::launch_composite(p, static_cast<cudaStream_t>(a->stream)); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "composite_kernel");
 }
 
@@ -203,7 +227,7 @@ int nrn_composite_backward(const NrnCompositeBwdArgs* a) {
   p.raw = a->raw; p.z = a->z_vals; p.rays_d = a->rays_d; p.rays_d_stride = a->rays_d_stride; p.noise = a->noise;
   p.n = a->n_rays; p.S = a->n_samples; p.C = a->channels; p.white_bkgd = a->white_bkgd;
   p.d_rgb = a->d_rgb_map; p.d_acc = a->d_acc_map; p.d_raw = a->d_raw;
-  cudaError_t e = nrn::launch_composite_bwd(p, static_cast<cudaStream_t>(a->stream));
+  cudaError_t e; { ScopedTimer tm(4, static_cast<cudaStream_t>(a->stream)); e = nrn::launch_composite_bwd(p, static_cast<cudaStream_t>(a->stream)); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "composite_bwd_kernel");
 }
 
@@ -259,12 +283,33 @@ int nrn_field_backward(const NrnFieldBwdArgs* a) {
   p.d_latents = a->d_latents; p.err = ds->err_word;
   e = nrn::launch_absmax(a->d_raw, p.P * a->out_ch, amax, st);
   if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
-  e = nrn::launch_field_bwd(p, bend, ds->num_sms, st);
+  { ScopedTimer tm(1, st); e = nrn::launch_field_bwd(p, bend, ds->num_sms, st); }
   if (e != cudaSuccess) return cuda_fail(e, "field_bwd_kernel");
   nrn::WgradParams w{};
   w.stash = p.stash; w.gstash = p.gstash; w.scratch = a->wgrad_scratch; w.amax = amax; w.n_tiles = p.n_tiles; w.err = ds->err_word;
-  e = nrn::launch_wgrad(w, bend, ds->num_sms, a->nerf_grad, nerf_n, a->bender_grad, bend_n, a->out_ch, st);
+  { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, bend, ds->num_sms, a->nerf_grad, nerf_n, a->bender_grad, bend_n, a->out_ch, st); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "wgrad_kernel");
+}
+
+int nrn_timing_enable(int on) {
+  for (int i = 0; i < g_timed_n; ++i) { cudaEventDestroy(g_timed[i].a); cudaEventDestroy(g_timed[i].b); }
+  g_timed_n = 0;
+  g_timing = on != 0;
+  return NRN_OK;
+}
+
+int nrn_timing_read(double* ms_sum, int* counts, int n_kinds) {
+  if (!ms_sum || !counts || n_kinds < 1) return fail(NRN_E_INVALID, "nrn_timing_read: bad arguments");
+  for (int k = 0; k < n_kinds; ++k) { ms_sum[k] = 0.0; counts[k] = 0; }
+  for (int i = 0; i < g_timed_n; ++i) {
+    cudaError_t e = cudaEventSynchronize(g_timed[i].b);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, g_timed[i].a, g_timed[i].b);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
+    if (g_timed[i].kind < n_kinds) { ms_sum[g_timed[i].kind] += ms; counts[g_timed[i].kind] += 1; }
+  }
+  return NRN_OK;
 }
 
 }  // extern "C"

@@ -1,0 +1,257 @@
+"""Ray-sharded multi-GPU execution: the replacement of torch.nn.DataParallel in the reference
+(train.py:290-297, :320-323; call sites train.py:1566-1577 and :473-480).
+
+One process per GPU (torchrun), `torch.distributed` with the NCCL backend.  The callables returned by
+get_parallelized_{training,render}_function keep DataParallel's calling convention (SURVEY.md
+appendix D): every tensor argument whose leading dimension is the ray count is split along dim 0
+(tensors nested in dicts / lists / tuples too), everything else is passed by reference, and the
+outputs are concatenated along dim 0 -- here with an all-gather, so that EVERY rank holds the full
+result and can keep executing the unmodified training loop in lock-step.
+
+Collectives on the path:
+  * inputs: one broadcast of the step's ray batch from rank 0 (ranks sample with unseeded numpy in
+    the reference, train.py:1546-1564; <= 3 MB), then each rank takes rows [r*ceil(N/G), (r+1)*ceil(N/G))
+  * outputs: all-gather of the per-ray losses [N] (training) or of the rendered maps (inference)
+  * gradients: ONE flat fp32 all-reduce (SUM) per optimizer step, issued from an optimizer
+    pre-step hook, i.e. after every backward pass of the iteration (the reference runs two when test
+    latents are optimised, train.py:1595-1608) has accumulated into .grad.
+Weights stay replicated; Adam runs identically on every rank.
+With world_size == 1 (or torch.distributed not initialised) the wrappers call straight through.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import run_nerf_helpers as H
+from . import train as T
+
+
+# ---------------------------------------------------------------------------------------------
+# distributed plumbing
+# ---------------------------------------------------------------------------------------------
+def _world() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _rank() -> int:
+    return dist.get_rank() if _world() > 1 else 0
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """DataParallel-style chunking: ceil(n / world) rows per rank, trailing ranks may get fewer/none."""
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def _map_tensors(obj: Any, fn: Callable[[torch.Tensor], Any]) -> Any:
+    if isinstance(obj, torch.Tensor):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: _map_tensors(v, fn) for k, v in obj.items()}
+    if isinstance(obj, tuple):
+        return tuple(_map_tensors(v, fn) for v in obj)
+    if isinstance(obj, list):
+        return [_map_tensors(v, fn) for v in obj]
+    return obj
+
+
+def _first_tensor(obj: Any) -> Optional[torch.Tensor]:
+    if isinstance(obj, torch.Tensor):
+        return obj
+    if isinstance(obj, dict):
+        obj = list(obj.values())
+    if isinstance(obj, (list, tuple)):
+        for v in obj:
+            t = _first_tensor(v)
+            if t is not None:
+                return t
+    return None
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """Concatenate per-rank row blocks (uneven allowed).  Backward: this rank's slice of the incoming
+    gradient -- every rank evaluates the same scalar loss on the gathered tensor, so no communication
+    is needed there; parameter gradients are summed later by the optimizer pre-step hook."""
+
+    @staticmethod
+    def forward(ctx, local: torch.Tensor, n_total: int):
+        world, rank = _world(), _rank()
+        per = (n_total + world - 1) // world
+        lo, hi = shard_bounds(n_total, world, rank)
+        ctx.bounds = (lo, hi)
+        pad = local.new_zeros((per,) + tuple(local.shape[1:]))
+        pad[: hi - lo] = local
+        out = local.new_empty((world * per,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, pad.contiguous()) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda else \
+            _all_gather_list(out, pad, world)
+        return out[:n_total]
+
+    @staticmethod
+    def backward(ctx, grad):
+        lo, hi = ctx.bounds
+        return grad[lo:hi].contiguous(), None
+
+
+def _all_gather_list(out, pad, world):
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad.contiguous())
+    out.copy_(torch.cat(parts, 0))
+
+
+def all_reduce_gradients(params: List[torch.Tensor]) -> None:
+    """One flat SUM all-reduce over the gradients of `params` (None gradients travel as zeros; a
+    per-parameter presence flag rides in the same buffer so that a gradient that is None on every
+    rank -- e.g. the dead views_linears, SURVEY.md 7.3-6 -- stays None)."""
+    if _world() == 1:
+        return
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return
+    dev = params[0].device
+    chunks = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
+    flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], dtype=torch.float32, device=dev)
+    flat = torch.cat(chunks + [flags])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    o = 0
+    flags = flat[-len(params):]
+    present = (flags > 0).tolist()
+    for p, here in zip(params, present):
+        n = p.numel()
+        if here:
+            g = flat[o:o + n].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+        o += n
+
+
+_HOOK_INSTALLED = False
+
+
+def _install_optimizer_hook() -> None:
+    """Global optimizer pre-step hook: all-reduce the gradients of everything the optimizer owns."""
+    global _HOOK_INSTALLED
+    if _HOOK_INSTALLED:
+        return
+    from torch.optim.optimizer import register_optimizer_step_pre_hook
+
+    def hook(optimizer, args, kwargs):
+        if _world() > 1:
+            all_reduce_gradients([p for g in optimizer.param_groups for p in g["params"]])
+
+    register_optimizer_step_pre_hook(hook)
+    _HOOK_INSTALLED = True
+
+
+class RayShardedFunction:
+    """Callable with nn.DataParallel's scatter / gather convention over torch.distributed ranks."""
+
+    def __init__(self, module: Callable, broadcast_inputs: bool = True):
+        self.module = module
+        self.broadcast_inputs = broadcast_inputs
+
+    def __call__(self, *args, **kwargs):
+        world, rank = _world(), _rank()
+        if world == 1:
+            return self.module(*args, **kwargs)
+        lead = _first_tensor(args)
+        if lead is None:
+            lead = _first_tensor(kwargs)
+        if lead is None:
+            raise RuntimeError("RayShardedFunction: no tensor argument to shard")
+        n = lead.shape[0]
+        lo, hi = shard_bounds(n, world, rank)
+
+        def shard(t: torch.Tensor):
+            if t.dim() == 0 or t.shape[0] != n:
+                return t
+            if self.broadcast_inputs and not t.requires_grad:
+                t = t.contiguous()
+                dist.broadcast(t, src=0)
+            return t[lo:hi]
+
+        out = self.module(*_map_tensors(args, shard), **_map_tensors(kwargs, shard))
+        return _map_tensors(out, lambda t: _AllGatherRows.apply(t, n))
+
+
+# ---------------------------------------------------------------------------------------------
+# the modules DataParallel used to wrap (train.py:140-287, :300-317)
+# ---------------------------------------------------------------------------------------------
+class training_wrapper_class(torch.nn.Module):
+    """Per-rank training step: latent lookup, render, data term and regularisers -> per-ray loss [N].
+    Mirrors training_wrapper_class.forward (train.py:152-287) argument for argument."""
+
+    def __init__(self, coarse_model, latents, fine_model=None, ray_bender=None):
+        super().__init__()
+        self.coarse_model = coarse_model
+        self.latents = latents            # python list of leaf tensors [Z] (train.py:1448-1453)
+        self.fine_model = fine_model
+        self.ray_bender = ray_bender
+
+    def forward(self, args, rays_o, rays_d, i, render_kwargs_train, target_s, global_step, start, dataset_extras,
+                batch_pixel_indices):
+        self.coarse_model.ray_bender = (self.ray_bender,)
+        render_kwargs_train["network_fn"] = self.coarse_model
+        render_kwargs_train["ray_bender"] = self.ray_bender
+        if self.fine_model is not None:
+            self.fine_model.ray_bender = (self.ray_bender,)
+            render_kwargs_train["network_fine"] = self.fine_model
+        dev = target_s.device
+        latent_table = torch.stack(self.latents, dim=0).to(dev)                      # [T, Z]
+        imageid_to_timestepid = torch.as_tensor(dataset_extras["imageid_to_timestepid"], device=dev)
+        n_rays = rays_o.shape[0]
+        timestep = imageid_to_timestepid[batch_pixel_indices[:, 0].to(dev).long()]
+        info = {"ray_bending_latents": latent_table[timestep, :]}                     # [N, Z]
+        detailed = args.offsets_loss_weight > 0.0 or args.divergence_loss_weight > 0.0
+        rgb, disp, acc, extras = T.render(rays_o, rays_d, chunk=args.chunk, verbose=i < 10, retraw=True,
+                                          additional_pixel_information=info, detailed_output=detailed, **render_kwargs_train)
+        loss = H.img2mse(rgb, target_s, n_rays)
+        if "rgb0" in extras:
+            loss = loss + H.img2mse(extras["rgb0"], target_s, n_rays)
+        sched = (1.0 / 100.0) ** (1 - (global_step / args.N_iters))                   # increasing schedule
+        if self.ray_bender is not None and args.offsets_loss_weight > 0.0:
+            w = extras["visibility_weights"].detach().reshape(-1)
+            off_norm = torch.norm(extras["unmasked_offsets"].reshape(-1, 3), dim=-1)
+            rig = extras["rigidity_mask"].reshape(-1)
+            offsets_loss = torch.mean((w * torch.pow(off_norm, 2.0 - rig)).view(n_rays, -1), dim=-1)
+            offsets_loss = offsets_loss + args.rigidity_loss_weight * torch.mean((w * rig).view(n_rays, -1), dim=-1)
+            loss = loss + args.offsets_loss_weight * sched * offsets_loss
+        if self.ray_bender is not None and args.divergence_loss_weight > 0.0:
+            pts = extras["initial_input_pts"].reshape(-1, 3)
+            lat = info["ray_bending_latents"]
+            lat = lat.view(n_rays, 1, -1).expand(n_rays, args.N_samples, lat.shape[-1]).reshape(-1, lat.shape[-1])
+            w = 1.0 - torch.exp(-F.relu(extras["opacity_alpha"].reshape(-1)))
+            div = H.compute_divergence_loss(extras["masked_offsets"].reshape(-1, 3), pts, lat, render_kwargs_train["ray_bender"],
+                                            exact=False, chunk=args.chunk, N_rays=n_rays, weights=w, backprop_into_weights=False)
+            loss = loss + args.divergence_loss_weight * sched * div
+        return loss
+
+
+class render_wrapper_class(torch.nn.Module):
+    def __init__(self, coarse_model, fine_model=None, ray_bender=None):
+        super().__init__()
+        self.coarse_model, self.fine_model, self.ray_bender = coarse_model, fine_model, ray_bender
+
+    def forward(self, *args, **kwargs):
+        self.coarse_model.ray_bender = (self.ray_bender,)
+        kwargs["network_fn"] = self.coarse_model
+        kwargs["ray_bender"] = self.ray_bender
+        if self.fine_model is not None:
+            self.fine_model.ray_bender = (self.ray_bender,)
+            kwargs["network_fine"] = self.fine_model
+        return T.render(*args, **kwargs)
+
+
+def get_parallelized_training_function(coarse_model, latents, fine_model=None, ray_bender=None):
+    _install_optimizer_hook()
+    return RayShardedFunction(training_wrapper_class(coarse_model, latents, fine_model=fine_model, ray_bender=ray_bender))
+
+
+def get_parallelized_render_function(coarse_model, fine_model=None, ray_bender=None):
+    return RayShardedFunction(render_wrapper_class(coarse_model, fine_model=fine_model, ray_bender=ray_bender))

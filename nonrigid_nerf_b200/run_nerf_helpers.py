@@ -180,3 +180,49 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
     out = ops.sample_pdf_op(bins.reshape(-1, bins.shape[-1]), weights.reshape(-1, weights.shape[-1]), N_samples,
                             None if u is None else u.reshape(-1, N_samples))
     return out.reshape(*lead, N_samples)
+
+
+# ---- divergence regulariser (run_nerf_helpers.py:22-116) --------------------------------------------
+# Stays PyTorch autograd over the SAME bender parameters: it needs d(offset)/d(xyz) differentiated a
+# second time w.r.t. the weights (double backward), which the first-order DGRAD/WGRAD kernels do not
+# serve.  ~3 % of the step's FLOPs, coarse samples only.
+def divergence_approx(input_points, offsets_of_inputs):
+    """Hutchinson estimator e^T J e of the trace of the offset field's Jacobian (FFJORD)."""
+    e = torch.randn_like(offsets_of_inputs)
+    e_dydx = torch.autograd.grad(offsets_of_inputs, input_points, e, create_graph=True)[0]
+    return (e_dydx * e).view(offsets_of_inputs.shape[0], -1).sum(dim=1)
+
+
+def _get_minibatch_jacobian(y, x):
+    """[N, D_y, D_x] Jacobian, one autograd pass per output dimension."""
+    assert y.shape[0] == x.shape[0]
+    y = y.view(y.shape[0], -1)
+    rows = []
+    for j in range(y.shape[1]):
+        dy = torch.autograd.grad(y[:, j], x, torch.ones_like(y[:, j]), retain_graph=True, create_graph=True)[0]
+        rows.append(dy.view(x.shape[0], 1, -1))
+    return torch.cat(rows, 1)
+
+
+def divergence_exact(input_points, offsets_of_inputs):
+    jac = _get_minibatch_jacobian(offsets_of_inputs, input_points)
+    return torch.diagonal(jac, dim1=1, dim2=2).sum(1)
+
+
+def compute_divergence_loss(offsets_of_inputs, input_points, point_latents, ray_bender, exact, chunk, N_rays, weights=None,
+                            backprop_into_weights=True):
+    """Per-ray mean over samples of weights * divergence(offset field)^2."""
+    divergence_fn = divergence_exact if exact else divergence_approx
+    input_points = input_points.detach().requires_grad_(True)
+    pieces = []
+    for i in range(0, input_points.shape[0], chunk):
+        sub = input_points[i:i + chunk, :]
+        details = ray_bender(sub, point_latents[i:i + chunk, :], special_loss_return=True)
+        offsets = details["masked_offsets"] if "masked_offsets" in details else details["unmasked_offsets"]
+        pieces.append(divergence_fn(sub, offsets))
+    div = torch.abs(torch.cat(pieces, dim=0)) ** 2
+    if weights is not None:
+        if not backprop_into_weights:
+            weights = weights.detach()
+        div = weights * div
+    return torch.mean(div.view(N_rays, -1), dim=-1)

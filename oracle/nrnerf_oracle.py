@@ -317,6 +317,22 @@ def training_loss(ret: Dict[str, Tensor], target: Tensor, offsets_w: float = 0.0
     return loss
 
 
+def divergence_loss(bp, ret: Dict[str, Tensor], latents: Tensor, n_rays: int, s_c: int, e: Optional[Tensor] = None) -> Tensor:
+    """Divergence regulariser of the offset field on the coarse samples (train.py:245-286 driving
+    compute_divergence_loss / divergence_approx, run_nerf_helpers.py:22-116): Hutchinson estimate
+    e^T J e with J = d(masked offsets)/d(xyz), squared, weighted by 1 - exp(-relu(alpha)) (detached),
+    mean over the ray's samples.  `e` ~ N(0, 1) [P, 3] may be injected."""
+    pts = ret["initial_input_pts"].reshape(-1, 3).detach().requires_grad_(True)
+    lat = latents[:, None, :].expand(n_rays, s_c, latents.shape[-1]).reshape(-1, latents.shape[-1])
+    w = (1.0 - torch.exp(-F.relu(ret["opacity_alpha"].reshape(-1)))).detach()
+    off = bender_forward(bp, pts, lat)["masked_offsets"]
+    if e is None:
+        e = torch.randn_like(off)
+    e_dydx = torch.autograd.grad(off, pts, e, create_graph=True)[0]
+    div = (e_dydx * e).view(off.shape[0], -1).sum(dim=1)
+    return torch.mean((w * torch.abs(div) ** 2).view(n_rays, -1), dim=-1)
+
+
 def clone_params(p, requires_grad=False):
     out = {}
     for k, v in p.items():
