@@ -136,7 +136,7 @@ def cpu_training_rate(n_rays, steps, warmup, threads):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 32)   # see cpu_baseline: more threads make the small-tensor ops slower
     sample = 256
     rate, sec = cpu_training_rate(sample, args.steps, args.warmup, threads)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n-rand", type=int, default=N_RAND, help="rays per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -194,7 +195,7 @@ def main():
     n_images = 86
     latents = [torch.zeros(32, device=dev).normal_(0, 0.1).requires_grad_(True) for _ in range(n_images)]
     grad_vars = latents + list(bender.parameters()) + list(coarse.parameters()) + list(fine.parameters())
-    optimizer = torch.optim.Adam(params=grad_vars, lr=5e-4, betas=(0.9, 0.999))
+    optimizer = torch.optim.Adam(params=grad_vars, lr=5e-4, betas=(0.9, 0.999), capturable=not args.no_graph)
     render_kwargs_train = {"network_query_fn": None, "perturb": 1.0, "N_importance": N_IMPORTANCE, "network_fine": fine,
                            "N_samples": N_SAMPLES, "network_fn": coarse, "ray_bender": bender, "use_viewdirs": False,
                            "white_bkgd": False, "raw_noise_std": 1.0, "ndc": False, "lindisp": False, "near": 0.0022, "far": 1.0024}
@@ -209,14 +210,27 @@ def main():
     pinned = [[torch.from_numpy(a).pin_memory() for a in b] for b in host]
     resident = [[t.to(dev) for t in b] for b in pinned]
 
-    def step(i, batch):
-        rays_o, rays_d, target, idx = batch
-        losses = train_fn(targs, rays_o, rays_d, i, render_kwargs_train, target, 1000 + i, 0, dataset_extras, idx)
+    def eager_step(rays_o, rays_d, target, idx):
+        losses = train_fn(targs, rays_o, rays_d, 100, render_kwargs_train, target, 1000, 0, dataset_extras, idx)
         loss = torch.mean(losses)
-        optimizer.zero_grad()
+        optimizer.zero_grad(set_to_none=True)
         loss.backward()
         optimizer.step()
         return loss
+
+    # the whole iteration (forward, losses, backward, all-reduce, Adam) is captured once and replayed
+    graphed = None
+    if not args.no_graph:
+        try:
+            from nonrigid_nerf_b200.graphs import GraphedStep
+            graphed = GraphedStep(eager_step, resident[0], warmup=3)
+        except Exception as exc:  # noqa: BLE001 - fall back to the eager loop, and say so in the JSON line
+            print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            graphed = None
+            torch.cuda.synchronize()
+
+    def step(i, batch):
+        return graphed(*batch) if graphed is not None else eager_step(*batch)
 
     def barrier():
         if world > 1:
@@ -246,11 +260,18 @@ def main():
     _lib.device_error_check()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    _lib.timing_enable(True)
+    if graphed is not None:
+        # re-capture with the per-kernel event records inside the graph (external event-record nodes)
+        _lib.timing_enable(True)
+        graphed = GraphedStep(eager_step, resident[0], warmup=1)
+        for i in range(3):
+            step(i, resident[i % pool])
+    else:
+        _lib.timing_enable(True)
     ms_total = timed(args.steps, e2e=False)
     kinds = _lib.timing_read()
-    _lib.timing_enable(False)
     ms_e2e = timed(args.steps, e2e=True)
+    _lib.timing_enable(False)
     clocks = sampler.stop() if sampler else None
     _lib.device_error_check()
 
@@ -263,8 +284,11 @@ def main():
     e2e_value = n_global * args.steps / (ms_e2e * 1e-3)
     peak, peak_src = read_peaks()
     # dominant kernel kind over the timed region (this rank), algorithmic FLOPs = points x 1,016,320 per launch pair
-    dom = max(("field_fwd", "field_dgrad", "wgrad"), key=lambda k: kinds[k][0])
-    dom_ms_per_step = kinds[dom][0] / args.steps
+    # launches per step of each kind: 2 (coarse + fine pass).  Eager: events of every step were recorded;
+    # graph replay: the captured event pairs hold the timestamps of the last replay of the timed region.
+    per_step = {k: (kinds[k][0] / (kinds[k][1] / 2.0) if kinds[k][1] else 0.0) for k in kinds}
+    dom = max(("field_fwd", "field_dgrad", "wgrad"), key=lambda k: per_step[k])
+    dom_ms_per_step = per_step[dom]
     flops_per_step = args.n_rand * POINTS_PER_RAY * FLOP_PER_POINT
     achieved = flops_per_step / (dom_ms_per_step * 1e-3) / 1e12
     line = {
@@ -278,14 +302,14 @@ def main():
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(sum(a.nbytes for a in host[0])),
                 "d2h_bytes_per_step": 4},
         "gpu_launches": 21 * args.steps,
-        "kernel_ms_per_step": {k: kinds[k][0] / args.steps for k in kinds},
+        "kernel_ms_per_step": per_step, "cuda_graph": graphed is not None,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
                      "note": "algorithmic FLOPs per step of this kernel kind (coarse + fine launch) = N_rand x 192 x 1,016,320"},
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = min(os.cpu_count() or 1, 32)   # PyTorch's CPU ops stop scaling (and regress) beyond a few dozen threads here
         rate, sec = cpu_training_rate(256, 3, 1, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
                                 "sample": "256-ray slice of the same training step, 1 warm-up + median of 3 steps"}

@@ -76,10 +76,17 @@ struct ScopedTimer {
     if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
     t.kind = kind;
     idx = g_timed_n++;
-    cudaEventRecord(t.a, st);
+    record(t.a);
   }
   ~ScopedTimer() {
-    if (idx >= 0) cudaEventRecord(g_timed[idx].b, st);
+    if (idx >= 0) record(g_timed[idx].b);
+  }
+  // inside a CUDA-graph capture the records become external event-record nodes: every replay of the graph
+  // re-stamps them, and the elapsed time of the last replay can be read afterwards
+  void record(cudaEvent_t ev) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    cudaEventRecordWithFlags(ev, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
   }
 };
 

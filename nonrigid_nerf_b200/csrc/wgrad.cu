@@ -124,20 +124,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
 
   if (warp == 0) {
     // ===================== producer: 64-row sub-images of dY and X =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < n_stages_total; ++it) {
-        const long long tile = t_begin + (it >> 1);
-        const int sub = it & 1;
+    // all 32 lanes issue bulk copies (one 1 KB chunk each per operand): a single lane issuing up to 64
+    // copies per stage would be the bottleneck of this HBM-bound kernel
+    uint32_t stage = 0, phase = 0;
+    for (int it = 0; it < n_stages_total; ++it) {
+      const long long tile = t_begin + (it >> 1);
+      const int sub = it & 1;
+      if (lane == 0) {
         W.wait(&sh->empty[stage], phase ^ 1u, 101);
-        uint8_t* dst = smem + stage * kStageBytes;
         mbar_arrive_expect_tx(&sh->full[stage], (a_chunks + b_chunks) * kSubChunk);
-        const uint8_t* ga = p.gstash + tile * kGradTileBytes + jb.a_off + sub * kSubChunk;
-        const uint8_t* gb = p.stash + tile * kStashTileBytes + jb.b_off + sub * kSubChunk;
-        for (int c = 0; c < a_chunks; ++c) tma_bulk_g2s(dst + c * kSubChunk, ga + c * kChunkBytes, kSubChunk, &sh->full[stage]);
-        for (int c = 0; c < b_chunks; ++c) tma_bulk_g2s(dst + (32 + c) * kSubChunk, gb + c * kChunkBytes, kSubChunk, &sh->full[stage]);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      uint8_t* dst = smem + stage * kStageBytes;
+      const uint8_t* ga = p.gstash + tile * kGradTileBytes + jb.a_off + sub * kSubChunk;
+      const uint8_t* gb = p.stash + tile * kStashTileBytes + jb.b_off + sub * kSubChunk;
+      if (lane < a_chunks) tma_bulk_g2s(dst + lane * kSubChunk, ga + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
+      if (lane < b_chunks) tma_bulk_g2s(dst + (32 + lane) * kSubChunk, gb + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
+      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================

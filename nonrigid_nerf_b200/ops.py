@@ -12,6 +12,7 @@ import torch
 from . import _lib
 
 LATENT = 32
+FORCE_PACK = False   # set while capturing a CUDA graph: the repack kernels must be part of the graph
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -63,7 +64,7 @@ def pack_nerf(net) -> torch.Tensor:
     ws, bs = nerf_param_list(net)
     key = _versions(ws + bs)
     cache = getattr(net, "_nrn_pack", None)
-    if cache is not None and cache[0] == key:
+    if cache is not None and cache[0] == key and not FORCE_PACK:
         return cache[1]
     lib = _lib.load()
     for t in ws + bs:
@@ -86,7 +87,7 @@ def pack_bender(bender) -> torch.Tensor:
     allp = net_w + net_b + rig_w + rig_b
     key = _versions(allp)
     cache = getattr(bender, "_nrn_pack", None)
-    if cache is not None and cache[0] == key:
+    if cache is not None and cache[0] == key and not FORCE_PACK:
         return cache[1]
     lib = _lib.load()
     for t in allp:

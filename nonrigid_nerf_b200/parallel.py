@@ -113,6 +113,18 @@ def all_reduce_gradients(params: List[torch.Tensor]) -> None:
     if not params:
         return
     dev = params[0].device
+    if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture no host read-back is possible: gradients that are None must be None on
+        # every rank (true for this path: the same graph runs everywhere), so only the present ones travel
+        live = [p for p in params if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1).float() for p in live])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        o = 0
+        for p in live:
+            n = p.numel()
+            p.grad.copy_(flat[o:o + n].view_as(p))
+            o += n
+        return
     chunks = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
     flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], dtype=torch.float32, device=dev)
     flat = torch.cat(chunks + [flags])
@@ -204,7 +216,10 @@ class training_wrapper_class(torch.nn.Module):
             render_kwargs_train["network_fine"] = self.fine_model
         dev = target_s.device
         latent_table = torch.stack(self.latents, dim=0).to(dev)                      # [T, Z]
-        imageid_to_timestepid = torch.as_tensor(dataset_extras["imageid_to_timestepid"], device=dev)
+        key = id(dataset_extras["imageid_to_timestepid"])
+        if getattr(self, "_i2t", (None, None))[0] != (key, dev):   # one H2D copy, not one per step (train.py:178-180)
+            self._i2t = ((key, dev), torch.as_tensor(dataset_extras["imageid_to_timestepid"], device=dev))
+        imageid_to_timestepid = self._i2t[1]
         n_rays = rays_o.shape[0]
         timestep = imageid_to_timestepid[batch_pixel_indices[:, 0].to(dev).long()]
         info = {"ray_bending_latents": latent_table[timestep, :]}                     # [N, Z]

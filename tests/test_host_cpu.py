@@ -1,0 +1,170 @@
+"""CPU-only tests: C-ABI surface, host-side mirror of the reference interface, ray-sharding plumbing
+(gloo, world_size 2).  No kernel is launched here."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from nonrigid_nerf_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "nrnerf_b200.h")).read()
+    declared = set(re.findall(r"\b(nrn_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS.keys()), declared ^ set(_lib.SYMBOLS.keys())
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = _lib.load()
+    assert loaded.nrn_abi_version() == _lib.ABI_VERSION
+    assert loaded.nrn_packed_nerf_bytes() > 2 * 990_000 and loaded.nrn_packed_bender_bytes() > 2 * 53_000
+    assert loaded.nrn_nerf_grad_floats(5) == 527_237 - 32_896 and loaded.nrn_bender_grad_floats() == 16_193
+    assert loaded.nrn_stash_bytes(1024, 64) == 512 * 634_880
+    assert loaded.nrn_stash_bytes(1, 7) == 2 * 634_880      # one ragged tile, rounded up to a tile pair
+
+
+def test_argument_validation_returns_error_codes_without_a_gpu():
+    from nonrigid_nerf_b200 import _lib
+    lib = _lib.load()
+    assert lib.nrn_field_forward(None) == -1
+    assert b"null args" in lib.nrn_last_error()
+    assert lib.nrn_sample_pdf(None, None, None, 4, 1, 8, None, None) == -1
+    assert lib.nrn_sample_coarse(None, None, -1, 64, 0, None, None) == -1
+    a = _lib.NrnCompositeArgs()
+    a.n_rays, a.n_samples, a.channels = 4, 64, 3
+    assert lib.nrn_composite(ctypes.byref(a)) == -1
+    with pytest.raises(RuntimeError):
+        _lib.check(-1, "unit test")
+
+
+def test_state_dict_keys_match_the_reference_checkpoint_layout():
+    from nonrigid_nerf_b200 import run_nerf_helpers as H
+    embed_fn, ch = H.get_embedder(10, 0)
+    assert ch == 63
+    bender = H.ray_bending(ch, 32, "simple_neural", embed_fn)
+    net = H.NeRF(D=8, W=256, input_ch=ch, output_ch=5, skips=[4], input_ch_views=0, use_viewdirs=False, ray_bender=bender,
+                 ray_bending_latent_size=32)
+    keys = list(net.state_dict().keys())
+    expect = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + \
+             ["views_linears.0.weight", "views_linears.0.bias", "output_linear.weight", "output_linear.bias"]
+    assert keys == expect
+    assert net.pts_linears[5].weight.shape == (256, 319) and net.output_linear.weight.shape == (5, 256)
+    assert sum(p.numel() for p in net.parameters()) == 527_237
+    bk = list(bender.state_dict().keys())
+    assert bk == [f"network.{i}.{k}" for i in range(4) for k in ("weight", "bias")] + ["network.4.weight"] + \
+        [f"rigidity_network.{i}.{k}" for i in range(3) for k in ("weight", "bias")]
+    assert sum(p.numel() for p in bender.parameters()) == 16_193
+    assert isinstance(net.ray_bender, tuple) and net.ray_bender[0] is bender       # 1-tuple API (run_nerf_helpers.py:213)
+    assert not any(p is q for p in net.parameters() for q in bender.parameters())
+    assert float(bender.network[4].weight.abs().sum()) == 0.0                      # straight rays at init
+    assert net.test_time_nonrigid_object_removal_threshold is None and bender.rigidity_test_time_cutoff is None
+
+
+def test_unsupported_configurations_raise_loudly():
+    from nonrigid_nerf_b200 import run_nerf_helpers as H, train as T
+    with pytest.raises(RuntimeError, match="use_viewdirs"):
+        H.NeRF(D=8, W=256, input_ch=63, use_viewdirs=True)
+    with pytest.raises(RuntimeError, match="time_conditioned"):
+        H.NeRF(D=8, W=256, input_ch=63, time_conditioned_baseline=True)
+    with pytest.raises(RuntimeError):
+        H.NeRF(D=4, W=128, input_ch=63)
+    with pytest.raises(RuntimeError):
+        H.get_embedder(10, -1)
+    o, d = torch.zeros(4, 3), torch.ones(4, 3)
+    with pytest.raises(RuntimeError, match="not implemented. change H, W, focal"):     # same message as train.py:386
+        T.render(o, d, ndc=True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        T.render(o, d, ndc=False, additional_pixel_information={"ray_bending_latents": torch.zeros(4, 32)})
+    with pytest.raises(RuntimeError, match="pytest"):
+        T.raw2outputs(torch.zeros(2, 4, 5), torch.zeros(2, 4), torch.ones(2, 3), pytest=True)
+
+
+def test_shard_bounds_follow_dataparallel_chunking():
+    from nonrigid_nerf_b200.parallel import shard_bounds
+    assert [shard_bounds(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [shard_bounds(2, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert shard_bounds(1024, 8, 7) == (896, 1024)
+
+
+# ---- world_size-2 gloo test of the DataParallel replacement -------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _ToyStep(torch.nn.Module):
+    """Stand-in for training_wrapper_class: per-ray loss from rays, a nested dict tensor and a shared net."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, rays, info, scale, target):
+        pred = self.net(torch.cat([rays, info["lat"]], -1))
+        return ((pred - target) ** 2).mean(-1) * scale
+
+
+def _worker(rank, world, port, n, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from nonrigid_nerf_b200 import parallel as P
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    dead = torch.nn.Parameter(torch.zeros(3))            # never used: its grad must stay None on every rank
+    opt = torch.optim.Adam(list(net.parameters()) + [dead], lr=1e-2)
+    P._install_optimizer_hook()
+    fn = P.RayShardedFunction(_ToyStep(net))
+    g = torch.Generator().manual_seed(7 + rank)          # ranks draw DIFFERENT batches; rank 0's must win
+    for it in range(3):
+        rays, lat, tgt = torch.randn(n, 3, generator=g), torch.randn(n, 2, generator=g), torch.randn(n, 3, generator=g)
+        losses = fn(rays, {"lat": lat}, 2.0, tgt)
+        assert losses.shape == (n,)
+        opt.zero_grad()
+        losses.mean().backward()
+        opt.step()
+    assert dead.grad is None
+    if rank == 0:
+        torch.save({"w": net[0].weight.detach().clone(), "losses": losses.detach().clone()}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ray_sharded_function_matches_single_process(tmp_path):
+    n, world = 11, 2          # uneven shards: 6 + 5 rows
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(world, _free_port(), n, out), nprocs=world, join=True)
+    got = torch.load(out)
+    # single-process run on rank 0's batches
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)
+    step = _ToyStep(net)
+    g = torch.Generator().manual_seed(7)
+    for it in range(3):
+        rays, lat, tgt = torch.randn(n, 3, generator=g), torch.randn(n, 2, generator=g), torch.randn(n, 3, generator=g)
+        losses = step(rays, {"lat": lat}, 2.0, tgt)
+        opt.zero_grad()
+        losses.mean().backward()
+        opt.step()
+    torch.testing.assert_close(got["losses"], losses.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got["w"], net[0].weight.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_single_process_wrappers_call_straight_through():
+    from nonrigid_nerf_b200 import parallel as P
+    net = torch.nn.Linear(5, 3)
+    fn = P.RayShardedFunction(_ToyStep(net))
+    out = fn(torch.randn(4, 3), {"lat": torch.randn(4, 2)}, 1.0, torch.randn(4, 3))
+    assert out.shape == (4,)

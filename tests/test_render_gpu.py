@@ -56,7 +56,7 @@ def test_render_matches_golden_caseB_and_keys():
     np.testing.assert_allclose(extras["z_std"].cpu().numpy(), g["z_std"], atol=2e-3)
     np.testing.assert_allclose(disp.cpu().numpy(), g["disp_map"], rtol=2e-2, atol=1e-3)
     np.testing.assert_allclose(extras["fine_rigidity_mask"][:16].cpu().numpy(), g["fine_rigidity_mask"], atol=3e-4)
-    np.testing.assert_allclose(extras["unmasked_offsets"][:16].cpu().numpy(), g["unmasked_offsets"], atol=2e-5)
+    np.testing.assert_allclose(extras["unmasked_offsets"][:16].cpu().numpy(), g["unmasked_offsets"], atol=1e-4)
     assert extras["raw"].shape == (n, 128, 5) and extras["fine_input_pts"].shape == (n, 128, 3)
 
 
