@@ -301,7 +301,7 @@ def main():
                    "l2": "per-step working set (activation + gradient stash ~1.9 GB) exceeds the 126 MB L2; 8 rotating input batches"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(sum(a.nbytes for a in host[0])),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": 21 * args.steps,
+        "gpu_launches": 28 * args.steps,
         "kernel_ms_per_step": per_step, "cuda_graph": graphed is not None,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,

@@ -150,10 +150,39 @@ typedef struct NrnFieldBwdArgs {
 } NrnFieldBwdArgs;
 int nrn_field_backward(const NrnFieldBwdArgs* args);
 
+/* ---- divergence regulariser of the offset field on the coarse samples: compute_divergence_loss /
+ * divergence_approx (run_nerf_helpers.py:22-116) as driven by train.py:245-286, forward and backward
+ * in closed form (no double backward).  Needs the coarse pass's activation stash. ---------------- */
+size_t nrn_div_stash_bytes(int n_rays, int n_samples);
+size_t nrn_div_grad_stash_bytes(int n_rays, int n_samples);
+typedef struct NrnDivArgs {
+  int32_t n_rays, n_samples;
+  const void* stash;               /* activation stash of the coarse nrn_field_forward call */
+  const float* e;                  /* [P][3] probe vectors ~ N(0, I) (torch.randn_like, run_nerf_helpers.py:110) */
+  const float* unmasked_offsets;   /* [P][3] coarse pass output */
+  const float* rigidity_mask;      /* [P]    coarse pass output */
+  const float* weights;            /* [P]    1 - exp(-relu(opacity_alpha)), detached (train.py:267) */
+  const float* const* net_w;       /* 5: ray_bending.network.i.weight (fp32, reference layout) */
+  const float* const* rig_w;       /* 3: ray_bending.rigidity_network.i.weight */
+  void* tangent_stash;             /* nrn_div_stash_bytes(): written by forward, read by backward */
+  float* d; float* alpha; float* beta; float* tau_c;   /* [P] each: written by forward, read by backward */
+  float* loss;                     /* forward out [n_rays]: mean over the ray's samples of weights * d^2 */
+  /* backward only */
+  const float* G;                  /* [P] dL/dd = g_ray * 2 * weights * d / n_samples */
+  void* adjoint_stash;             /* workspace, nrn_div_grad_stash_bytes() */
+  float* wgrad_scratch;            /* workspace, nrn_wgrad_scratch_bytes() */
+  float* d_unmasked_offsets;       /* out [P][3] gradient w.r.t. the coarse unmasked offsets */
+  float* d_rigidity_mask;          /* out [P]    gradient w.r.t. the coarse rigidity mask */
+  float* bender_grad;              /* out, nrn_bender_grad_floats(): weight gradients of the tangent chain */
+  void* stream;
+} NrnDivArgs;
+int nrn_divergence_forward(const NrnDivArgs* args);
+int nrn_divergence_backward(const NrnDivArgs* args);
+
 /* ---- optional per-kernel timing (measurement aid for bench.py) ---------------------------------
  * While enabled, every launch of the kernel kinds below is bracketed by CUDA events recorded on the
  * launch stream.  kinds: 0 field forward, 1 field DGRAD, 2 WGRAD (+reduce), 3 composite(+resample),
- * 4 composite backward.  nrn_timing_read synchronises the recorded events and returns per-kind sums. */
+ * 4 composite backward, 5 divergence regulariser.  nrn_timing_read synchronises the recorded events and returns per-kind sums. */
 int nrn_timing_enable(int on);
 int nrn_timing_read(double* ms_sum, int* counts, int n_kinds);
 

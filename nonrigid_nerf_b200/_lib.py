@@ -47,6 +47,18 @@ class NrnFieldBwdArgs(C.Structure):
     ]
 
 
+class NrnDivArgs(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int32), ("n_samples", C.c_int32),
+        ("stash", _vp), ("e", _vp), ("unmasked_offsets", _vp), ("rigidity_mask", _vp), ("weights", _vp),
+        ("net_w", C.POINTER(_vp)), ("rig_w", C.POINTER(_vp)),
+        ("tangent_stash", _vp), ("d", _vp), ("alpha", _vp), ("beta", _vp), ("tau_c", _vp), ("loss", _vp),
+        ("G", _vp), ("adjoint_stash", _vp), ("wgrad_scratch", _vp), ("d_unmasked_offsets", _vp), ("d_rigidity_mask", _vp),
+        ("bender_grad", _vp),
+        ("stream", _vp),
+    ]
+
+
 class NrnCompositeArgs(C.Structure):
     _fields_ = [
         ("raw", _vp), ("z_vals", _vp), ("rays_d", _vp), ("rays_d_stride", C.c_int32), ("noise", _vp),
@@ -86,11 +98,15 @@ SYMBOLS = {
     "nrn_nerf_grad_floats": (C.c_int, [C.c_int]),
     "nrn_bender_grad_floats": (C.c_int, []),
     "nrn_field_backward": (C.c_int, [C.POINTER(NrnFieldBwdArgs)]),
+    "nrn_div_stash_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nrn_div_grad_stash_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nrn_divergence_forward": (C.c_int, [C.POINTER(NrnDivArgs)]),
+    "nrn_divergence_backward": (C.c_int, [C.POINTER(NrnDivArgs)]),
     "nrn_timing_enable": (C.c_int, [C.c_int]),
     "nrn_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }
 
-KERNEL_KINDS = ("field_fwd", "field_dgrad", "wgrad", "composite", "composite_bwd")
+KERNEL_KINDS = ("field_fwd", "field_dgrad", "wgrad", "composite", "composite_bwd", "divergence")
 
 
 def timing_enable(on: bool) -> None:

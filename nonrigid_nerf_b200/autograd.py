@@ -81,6 +81,7 @@ class _FieldTrainFn(torch.autograd.Function):
         ctx.params = params
         ctx.set_materialize_grads(False)
         if bender is not None:
+            _register_stash(det["unmasked_offsets"], stash)
             ctx.save_for_backward(det["unmasked_offsets"], det["rigidity_mask"])
             outs = (raw, det["unmasked_offsets"], det["rigidity_mask"], det["initial_input_pts"], det["input_pts"],
                     det["masked_offsets"])
@@ -146,6 +147,121 @@ class _FieldTrainFn(torch.autograd.Function):
             grads += _split_flat(bend_grad, bend_p)
         grads = [g if p.requires_grad else None for g, p in zip(grads, ctx.params)]
         return (None, None, None, d_lat, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------------
+# divergence regulariser (fused)
+# ---------------------------------------------------------------------------------------------
+_STASH_BY_PTR = {}   # data_ptr of a coarse pass's unmasked_offsets -> weakref to that pass's activation stash
+
+
+def _register_stash(unmasked: torch.Tensor, stash: torch.Tensor) -> None:
+    import weakref
+    for k in [k for k, v in _STASH_BY_PTR.items() if v() is None]:
+        del _STASH_BY_PTR[k]
+    _STASH_BY_PTR[unmasked.data_ptr()] = weakref.ref(stash)
+
+
+def lookup_stash(unmasked: torch.Tensor) -> Optional[torch.Tensor]:
+    ref = _STASH_BY_PTR.get(unmasked.data_ptr())
+    return ref() if ref is not None else None
+
+
+class _DivergenceFn(torch.autograd.Function):
+    """per-ray mean_s(w * (e^T J e)^2) of the offset field, closed-form forward and backward (csrc/div.cu)."""
+
+    @staticmethod
+    def forward(ctx, unmasked, rigidity, weights, e, stash, bender, *bender_params):
+        n, s = unmasked.shape[0], unmasked.shape[1]
+        dev = unmasked.device
+        lib = _lib.load()
+        a = _lib.NrnDivArgs()
+        a.n_rays, a.n_samples = n, s
+        un = unmasked.detach().contiguous().float()
+        rg = rigidity.detach().contiguous().float()
+        w = weights.detach().contiguous().float()
+        e = e.contiguous().float()
+        net_w, _, rig_w, _ = ops.bender_param_list(bender)
+        net_arr = ops._ptr_array([t.detach() for t in net_w])
+        rig_arr = ops._ptr_array([t.detach() for t in rig_w])
+        tan = torch.empty(lib.nrn_div_stash_bytes(n, s), dtype=torch.uint8, device=dev)
+        scal = torch.empty(4, n * s, dtype=torch.float32, device=dev)
+        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        a.stash, a.e, a.unmasked_offsets, a.rigidity_mask, a.weights = stash.data_ptr(), e.data_ptr(), un.data_ptr(), rg.data_ptr(), w.data_ptr()
+        a.net_w, a.rig_w = net_arr, rig_arr
+        a.tangent_stash = tan.data_ptr()
+        a.d, a.alpha, a.beta, a.tau_c = (scal[i].data_ptr() for i in range(4))
+        a.loss = loss.data_ptr()
+        a.stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrn_divergence_forward(C.byref(a)), "divergence_forward")
+        ctx.keep = (un, rg, w, e, stash, tan, scal, bender)
+        ctx.params = bender_params
+        ctx.shape = (n, s)
+        ctx.in_shapes = (unmasked.shape, rigidity.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        un, rg, w, e, stash, tan, scal, bender = ctx.keep
+        n, s = ctx.shape
+        dev = un.device
+        lib = _lib.load()
+        # G = dL/dd per point = g_ray * 2 * w * d / S
+        G = (g.reshape(n, 1).float() * (2.0 / s)) * w.reshape(n, s) * scal[0].reshape(n, s)
+        G = G.contiguous()
+        a = _lib.NrnDivArgs()
+        a.n_rays, a.n_samples = n, s
+        net_w, _, rig_w, _ = ops.bender_param_list(bender)
+        net_arr = ops._ptr_array([t.detach() for t in net_w])
+        rig_arr = ops._ptr_array([t.detach() for t in rig_w])
+        a.stash, a.e, a.unmasked_offsets, a.rigidity_mask, a.weights = stash.data_ptr(), e.data_ptr(), un.data_ptr(), rg.data_ptr(), w.data_ptr()
+        a.net_w, a.rig_w = net_arr, rig_arr
+        a.tangent_stash = tan.data_ptr()
+        a.d, a.alpha, a.beta, a.tau_c = (scal[i].data_ptr() for i in range(4))
+        a.G = G.data_ptr()
+        adj = torch.empty(lib.nrn_div_grad_stash_bytes(n, s), dtype=torch.uint8, device=dev)
+        scratch = torch.empty(lib.nrn_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
+        d_un = torch.empty(n * s, 3, dtype=torch.float32, device=dev)
+        d_rg = torch.empty(n * s, dtype=torch.float32, device=dev)
+        bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
+        a.adjoint_stash, a.wgrad_scratch = adj.data_ptr(), scratch.data_ptr()
+        a.d_unmasked_offsets, a.d_rigidity_mask, a.bender_grad = d_un.data_ptr(), d_rg.data_ptr(), bend_grad.data_ptr()
+        a.stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrn_divergence_backward(C.byref(a)), "divergence_backward")
+        grads = _split_flat(bend_grad, ctx.params)
+        grads = [gr if p.requires_grad else None for gr, p in zip(grads, ctx.params)]
+        ctx.keep = None
+        return (d_un.view(ctx.in_shapes[0]), d_rg.view(ctx.in_shapes[1]), None, None, None, None, *grads)
+
+
+def divergence_loss(unmasked: torch.Tensor, rigidity: torch.Tensor, weights: torch.Tensor, bender,
+                    e: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused divergence regulariser on the coarse samples of the LAST differentiable coarse pass.
+    unmasked [N,S,3], rigidity [N,S,1] must be that pass's outputs (they locate its activation stash and
+    carry the gradient w.r.t. the primal bender evaluation); weights [N,S] are used detached; `e` [N*S,3]
+    are the Hutchinson probes (drawn with torch.randn like run_nerf_helpers.py:110 when None)."""
+    stash = lookup_stash(unmasked)
+    if stash is None:
+        raise RuntimeError("nonrigid_nerf_b200: no activation stash for these offsets -- the fused divergence term needs the "
+                           "un-chunked coarse pass of the current differentiable render() call (N_rand <= chunk)")
+    n, s = unmasked.shape[0], unmasked.shape[1]
+    if e is None:
+        e = torch.randn(n * s, 3, device=unmasked.device)
+    _, bend_p = _flat_params_bender(bender)
+    return _DivergenceFn.apply(unmasked, rigidity, weights, e, stash, bender, *bend_p)
+
+
+def _flat_params_bender(bender):
+    net_w, net_b, rig_w, rig_b = ops.bender_param_list(bender)
+    bend = []
+    for i in range(4):
+        bend += [net_w[i], net_b[i]]
+    bend.append(net_w[4])
+    for i in range(3):
+        bend += [rig_w[i], rig_b[i]]
+    return None, bend
 
 
 class _CompositeFn(torch.autograd.Function):

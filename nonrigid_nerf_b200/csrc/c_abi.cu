@@ -8,6 +8,7 @@
 #include "pack.cuh"
 #include "ray_ops.cuh"
 #include "wgrad.cuh"
+#include "div.cuh"
 
 namespace nrn {
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
@@ -296,6 +297,66 @@ int nrn_field_backward(const NrnFieldBwdArgs* a) {
   w.stash = p.stash; w.gstash = p.gstash; w.scratch = a->wgrad_scratch; w.amax = amax; w.n_tiles = p.n_tiles; w.err = ds->err_word;
   { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, bend, ds->num_sms, a->nerf_grad, nerf_n, a->bender_grad, bend_n, a->out_ch, st); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "wgrad_kernel");
+}
+
+static long long point_tiles(int n_rays, int n_samples) {
+  return (static_cast<long long>(n_rays) * n_samples + nrn::kTileM - 1) / nrn::kTileM;
+}
+size_t nrn_div_stash_bytes(int n_rays, int n_samples) { return static_cast<size_t>(point_tiles(n_rays, n_samples)) * nrn::kTanTileBytes; }
+size_t nrn_div_grad_stash_bytes(int n_rays, int n_samples) { return static_cast<size_t>(point_tiles(n_rays, n_samples)) * nrn::kAdjTileBytes; }
+
+static int fill_div(const NrnDivArgs* a, nrn::DivParams& p, const char* who) {
+  if (!a) return fail(NRN_E_INVALID, "%s: null args", who);
+  if (a->n_rays < 0 || a->n_samples < 1) return fail(NRN_E_INVALID, "%s: bad sizes", who);
+  if (!a->stash || !a->e || !a->unmasked_offsets || !a->rigidity_mask || !a->weights || !a->net_w || !a->rig_w || !a->tangent_stash ||
+      !a->d || !a->alpha || !a->beta || !a->tau_c)
+    return fail(NRN_E_INVALID, "%s: null argument", who);
+  p.P = static_cast<long long>(a->n_rays) * a->n_samples;
+  p.S = a->n_samples; p.n_rays = a->n_rays;
+  p.stash = static_cast<const uint8_t*>(a->stash);
+  p.e = a->e; p.unmasked = a->unmasked_offsets; p.rigidity = a->rigidity_mask; p.w = a->weights;
+  for (int i = 0; i < 5; ++i) { if (!a->net_w[i]) return fail(NRN_E_INVALID, "%s: null weight", who); p.net_w[i] = a->net_w[i]; }
+  for (int i = 0; i < 3; ++i) { if (!a->rig_w[i]) return fail(NRN_E_INVALID, "%s: null weight", who); p.rig_w[i] = a->rig_w[i]; }
+  p.tan = static_cast<uint8_t*>(a->tangent_stash);
+  p.d = a->d; p.adot = a->alpha; p.beta = a->beta; p.tauc = a->tau_c;
+  return NRN_OK;
+}
+
+int nrn_divergence_forward(const NrnDivArgs* a) {
+  nrn::DivParams p{};
+  int rc = fill_div(a, p, "nrn_divergence_forward");
+  if (rc) return rc;
+  if (!a->loss) return fail(NRN_E_INVALID, "nrn_divergence_forward: null loss");
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  cudaError_t e = cudaMemsetAsync(a->loss, 0, sizeof(float) * static_cast<size_t>(a->n_rays), st);
+  if (e != cudaSuccess) return cuda_fail(e, "memset loss");
+  p.loss = a->loss;
+  { ScopedTimer tm(5, st); e = nrn::launch_div_fwd(p, st); }
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "div_fwd_kernel");
+}
+
+int nrn_divergence_backward(const NrnDivArgs* a) {
+  nrn::DivParams p{};
+  int rc = fill_div(a, p, "nrn_divergence_backward");
+  if (rc) return rc;
+  if (!a->G || !a->adjoint_stash || !a->wgrad_scratch || !a->d_unmasked_offsets || !a->d_rigidity_mask || !a->bender_grad)
+    return fail(NRN_E_INVALID, "nrn_divergence_backward: null argument");
+  DeviceState* ds;
+  rc = device_state(&ds);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+  float* amax = reinterpret_cast<float*>(ds->err_word + 2);
+  p.G = a->G; p.amax = amax; p.adj = static_cast<uint8_t*>(a->adjoint_stash);
+  p.d_unmasked = a->d_unmasked_offsets; p.d_rigid = a->d_rigidity_mask;
+  cudaError_t e = nrn::launch_absmax(a->G, p.P, amax, st);
+  if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
+  { ScopedTimer tm(5, st); e = nrn::launch_div_bwd(p, st); }
+  if (e != cudaSuccess) return cuda_fail(e, "div_bwd_kernel");
+  nrn::WgradParams w{};
+  w.stash = p.tan; w.gstash = p.adj; w.scratch = a->wgrad_scratch; w.amax = amax; w.compact = 1;
+  w.n_tiles = static_cast<int>((p.P + nrn::kTileM - 1) / nrn::kTileM); w.err = ds->err_word;
+  { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, true, ds->num_sms, nullptr, 0, a->bender_grad, nrn_bender_grad_floats(), 5, st); }
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "wgrad_kernel (divergence)");
 }
 
 int nrn_timing_enable(int on) {

@@ -75,6 +75,9 @@ constexpr int kGsYb2 = kGsYb3 + 8 * kChunkBytes;           // 10 chunks (64 + ri
 constexpr int kGsYb1 = kGsYb2 + 10 * kChunkBytes;          // 12 chunks
 constexpr int kGsYb0 = kGsYb1 + 12 * kChunkBytes;          // 12 chunks
 constexpr int kGradTileBytes = kGsYb0 + 12 * kChunkBytes;  // 618,496
+// compact stashes of the divergence regulariser (div.cu): only the bender images, same relative order
+constexpr int kTanTileBytes = kStashTileBytes - kStBin;    // 94,208: [e | t1 s1 | t2 s2 | t3 | t4]
+constexpr int kAdjTileBytes = kGradTileBytes - kGsYb4;     // 90,112: adjoints of the tangent chain
 
 // ------------------------------------------------------------------------------------------
 // Transposed weight images for DGRAD (dX = dY . W: B operand = W^T, rows = input features,

@@ -7,12 +7,17 @@
 // DGRAD (gradient stash) kernels; read MN-major they are exactly the transposed operands WGRAD needs
 // (sm100_ptx.cuh), so no transpose pass exists.  The contraction runs over points (K = 128 per tile).
 //
-// Decomposition: a fixed list of jobs (one per layer, table below); every job is split over a
-// contiguous range of tiles per CTA ("split-K"), partial sums go to a scratch buffer and a second
-// kernel reduces them in a fixed order (deterministic) while un-padding / un-permuting into the
-// reference's parameter layout and dividing out the loss scale.
-// This kernel is HBM-bound (each stash byte is used for 256 MACs ~ 4x below the ridge): the warps not
-// needed for TMA / MMA issue compute the bias gradient from the same shared-memory stage.
+// Decomposition: a fixed list of jobs; a job is a set of up to three "sub-MMAs" that share one
+// shared-memory stage (jobs 0-9: one NeRF layer, two 128-row halves of dW; jobs 10-11: the five small
+// ray-bender layers grouped so that every job moves 40-64 KB per stage).  Every job is split over
+// contiguous tile ranges ("split-K") proportionally to its bytes; partial sums go to a scratch buffer
+// and a second kernel reduces them in a fixed order (deterministic) while un-padding / un-permuting
+// into the reference's parameter layout and dividing out the loss scale.
+// The kernel is HBM-bound (each stash byte feeds 256 MACs, ~4x below the ridge): the warps not needed
+// for TMA / MMA issue compute the bias gradient from the same shared-memory stage.
+//
+// Compact mode (WgradParams.compact): the same two bender jobs over the tangent / adjoint stashes of
+// the divergence regulariser (div.cu), which hold only the bender images.
 #include "nrn_common.cuh"
 #include "sm100_ptx.cuh"
 #include "wgrad.cuh"
@@ -25,28 +30,64 @@ constexpr long long kWaitLimitCycles = 1ll << 28;
 constexpr int kWgStages = 3;
 constexpr int kSubRows = 64;                       // points per pipeline stage
 constexpr int kSubChunk = kSubRows * 16;           // 1 KB per chunk of a 64-row sub-image
-constexpr int kStageBytes = 64 * kSubChunk;        // up to 32 A chunks + 32 B chunks
+constexpr int kStageBytes = 64 * kSubChunk;        // up to 64 chunks (A images first, then B images)
 constexpr int kWgThreads = 320;                    // producer, mma, 8 bias/drain warps
 
+struct Sub {
+  int a_chunk, b_chunk, n, tmem_col;  // operand chunk offsets inside the stage, N, accumulator column
+  int a_cols;                         // valid rows of the 128-row accumulator
+};
 struct Job {
-  int a_off, a_cols;   // dY image in the gradient stash (M = output features)
-  int b_off, b_cols;   // X image in the activation stash (N = input features)
-  int bias;            // compute column sums of A (bias gradient)
+  int n_imgs;            // number of (A,B) image pairs streamed per stage
+  int a_off[3], a_chunks[3];
+  int b_off[3], b_chunks[3];
+  int n_sub;
+  Sub sub[3];
+  int bias;              // compute column sums over all A chunks
+  int a_total, b_total;  // chunks
 };
 
-// job ids: 0 head, 1..7 = L1..L7 (input h_l), 8 L5e, 9 L0, 10..14 = B4, B3, B2, B1, B0
-__device__ __forceinline__ Job job_desc(int j) {
-  switch (j) {
-    case 0: return {kGsRaw, 16, kStH + 7 * kHBytes, 256, 1};
-    case 8: return {kGsY + 5 * kHBytes, 256, kStE, 64, 0};
-    case 9: return {kGsY + 0 * kHBytes, 256, kStE, 64, 1};
-    case 10: return {kGsYb4, 16, kStHb4, 64, 0};
-    case 11: return {kGsYb3, 64, kStHb3, 64, 1};
-    case 12: return {kGsYb2, 80, kStHb2, 96, 1};
-    case 13: return {kGsYb1, 96, kStHb1, 96, 1};
-    case 14: return {kGsYb0, 96, kStBin, 48, 1};
-    default: return {kGsY + j * kHBytes, 256, kStH + (j - 1) * kHBytes, 256, 1};  // L_j, j = 1..7
+// job ids: 0 head, 1..7 = L1..L7 (input h_l), 8 L5e, 9 L0, 10 = {B4,B3,B2}, 11 = {B1,B0}
+__device__ __forceinline__ Job job_desc(int j, int compact) {
+  Job jb{};
+  if (j <= 9) {
+    int a_off, a_cols, b_off, b_cols, bias = 1;
+    if (j == 0) { a_off = kGsRaw; a_cols = 16; b_off = kStH + 7 * kHBytes; b_cols = 256; }
+    else if (j == 8) { a_off = kGsY + 5 * kHBytes; a_cols = 256; b_off = kStE; b_cols = 64; bias = 0; }
+    else if (j == 9) { a_off = kGsY; a_cols = 256; b_off = kStE; b_cols = 64; }
+    else { a_off = kGsY + j * kHBytes; a_cols = 256; b_off = kStH + (j - 1) * kHBytes; b_cols = 256; }
+    jb.n_imgs = 1;
+    jb.a_off[0] = a_off; jb.a_chunks[0] = a_cols / 8; jb.b_off[0] = b_off; jb.b_chunks[0] = b_cols / 8;
+    jb.a_total = a_cols / 8; jb.b_total = b_cols / 8;
+    jb.n_sub = a_cols > 128 ? 2 : 1;
+    jb.sub[0] = {0, jb.a_total, b_cols, 0, a_cols > 128 ? 128 : a_cols};
+    jb.sub[1] = {16, jb.a_total, b_cols, 256, 128};
+    jb.bias = bias;
+    return jb;
   }
+  // bender jobs; in compact mode the stashes hold only the bender images
+  const int ga = compact ? kGsYb4 : 0, sa = compact ? kStBin : 0;
+  if (j == 10) {
+    jb.n_imgs = 3;
+    jb.a_off[0] = kGsYb4 - ga; jb.a_chunks[0] = 2;  jb.b_off[0] = kStHb4 - sa; jb.b_chunks[0] = 8;
+    jb.a_off[1] = kGsYb3 - ga; jb.a_chunks[1] = 8;  jb.b_off[1] = kStHb3 - sa; jb.b_chunks[1] = 8;
+    jb.a_off[2] = kGsYb2 - ga; jb.a_chunks[2] = 10; jb.b_off[2] = kStHb2 - sa; jb.b_chunks[2] = 12;
+    jb.a_total = 20; jb.b_total = 28;
+    jb.n_sub = 3;
+    jb.sub[0] = {0, 20, 64, 0, 16};
+    jb.sub[1] = {2, 28, 64, 64, 64};
+    jb.sub[2] = {10, 36, 96, 128, 80};
+  } else {
+    jb.n_imgs = 2;
+    jb.a_off[0] = kGsYb1 - ga; jb.a_chunks[0] = 12; jb.b_off[0] = kStHb1 - sa; jb.b_chunks[0] = 12;
+    jb.a_off[1] = kGsYb0 - ga; jb.a_chunks[1] = 12; jb.b_off[1] = kStBin - sa; jb.b_chunks[1] = 6;
+    jb.a_total = 24; jb.b_total = 18;
+    jb.n_sub = 2;
+    jb.sub[0] = {0, 24, 96, 0, 96};
+    jb.sub[1] = {12, 36, 48, 96, 96};
+  }
+  jb.bias = compact ? 0 : 1;   // the tangent chain of the divergence term has no bias
+  return jb;
 }
 
 struct Shared {
@@ -75,11 +116,11 @@ struct Waiter {
   }
 };
 
-// which (job, split) does this CTA own?  splits[] comes from the host (WgradParams)
+// which (job, split) does this CTA own?  job_ids[] / splits[] come from the host (WgradParams)
 __device__ __forceinline__ bool locate(const WgradParams& p, int cta, int& job, int& split, int& nsplit) {
   int base = 0;
   for (int j = 0; j < p.n_jobs; ++j) {
-    if (cta < base + p.splits[j]) { job = j; split = cta - base; nsplit = p.splits[j]; return true; }
+    if (cta < base + p.splits[j]) { job = p.job_ids[j]; split = cta - base; nsplit = p.splits[j]; return true; }
     base += p.splits[j];
   }
   return false;
@@ -94,9 +135,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
 
   int job_id = 0, split = 0, nsplit = 1;
   const bool have = locate(p, blockIdx.x, job_id, split, nsplit);
-  const Job jb = job_desc(job_id);
-  const int a_chunks = jb.a_cols / 8, b_chunks = jb.b_cols / 8;
-  const int m_halves = jb.a_cols > 128 ? 2 : 1;
+  const Job jb = job_desc(job_id, p.compact);
   // contiguous tile range of this split
   const int per = (p.n_tiles + nsplit - 1) / nsplit;
   const int t_begin = have ? min(split * per, p.n_tiles) : 0;
@@ -124,40 +163,47 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
 
   if (warp == 0) {
     // ===================== producer: 64-row sub-images of dY and X =====================
-    // all 32 lanes issue bulk copies (one 1 KB chunk each per operand): a single lane issuing up to 64
-    // copies per stage would be the bottleneck of this HBM-bound kernel
+    // all 32 lanes issue bulk copies (1 KB chunk each): a single lane issuing up to 64 copies per stage
+    // would be the bottleneck of this HBM-bound kernel
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < n_stages_total; ++it) {
       const long long tile = t_begin + (it >> 1);
       const int sub = it & 1;
       if (lane == 0) {
         W.wait(&sh->empty[stage], phase ^ 1u, 101);
-        mbar_arrive_expect_tx(&sh->full[stage], (a_chunks + b_chunks) * kSubChunk);
+        mbar_arrive_expect_tx(&sh->full[stage], (jb.a_total + jb.b_total) * kSubChunk);
       }
       __syncwarp();
       uint8_t* dst = smem + stage * kStageBytes;
-      const uint8_t* ga = p.gstash + tile * kGradTileBytes + jb.a_off + sub * kSubChunk;
-      const uint8_t* gb = p.stash + tile * kStashTileBytes + jb.b_off + sub * kSubChunk;
-      if (lane < a_chunks) tma_bulk_g2s(dst + lane * kSubChunk, ga + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
-      if (lane < b_chunks) tma_bulk_g2s(dst + (32 + lane) * kSubChunk, gb + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
+      const uint8_t* ga = p.gstash + tile * p.gstash_tile_bytes + sub * kSubChunk;
+      const uint8_t* gb = p.stash + tile * p.stash_tile_bytes + sub * kSubChunk;
+      int ca = 0, cb = jb.a_total;
+      for (int im = 0; im < jb.n_imgs; ++im) {
+        if (lane < jb.a_chunks[im])
+          tma_bulk_g2s(dst + (ca + lane) * kSubChunk, ga + jb.a_off[im] + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
+        if (lane < jb.b_chunks[im])
+          tma_bulk_g2s(dst + (cb + lane) * kSubChunk, gb + jb.b_off[im] + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
+        ca += jb.a_chunks[im];
+        cb += jb.b_chunks[im];
+      }
       if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const uint32_t idesc = umma_instr_desc(128, jb.b_cols, UMMA_F16, UMMA_F16, UMMA_MN_MAJOR, UMMA_MN_MAJOR);
       for (int it = 0; it < n_stages_total; ++it) {
         W.wait(&sh->full[stage], phase, 201);
         tc_fence_after_sync();
-        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-        const uint32_t sb = sa + 32 * kSubChunk;
-        for (int mh = 0; mh < m_halves; ++mh) {
+        const uint32_t s0 = smem_u32(smem + stage * kStageBytes);
+        for (int s = 0; s < jb.n_sub; ++s) {
+          const Sub sb = jb.sub[s];
+          const uint32_t idesc = umma_instr_desc(128, sb.n, UMMA_F16, UMMA_F16, UMMA_MN_MAJOR, UMMA_MN_MAJOR);
           // MN-major: SBO = stride between 8-feature chunks, LBO = stride between 8-point groups
-          const uint64_t adesc = umma_smem_desc(sa + mh * 16 * kSubChunk, 128, kSubChunk);
-          const uint64_t bdesc = umma_smem_desc(sb, 128, kSubChunk);
+          const uint64_t adesc = umma_smem_desc(s0 + sb.a_chunk * kSubChunk, 128, kSubChunk);
+          const uint64_t bdesc = umma_smem_desc(s0 + sb.b_chunk * kSubChunk, 128, kSubChunk);
           for (int k = 0; k < kSubRows / 16; ++k) {
-            umma_f16_ss(tmem_base + mh * 256, umma_desc_advance(adesc, k * 256), umma_desc_advance(bdesc, k * 256), idesc,
+            umma_f16_ss(tmem_base + sb.tmem_col, umma_desc_advance(adesc, k * 256), umma_desc_advance(bdesc, k * 256), idesc,
                         (it | k) ? 1u : 0u);
           }
         }
@@ -174,8 +220,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < n_stages_total; ++it) {
       W.wait(&sh->full[stage], phase, 301);
-      if (jb.bias) {   // warp-uniform; lanes whose chunk lies beyond the image contribute zeros
-        const bool live = c < a_chunks;
+      if (jb.bias) {   // warp-uniform; lanes whose chunk lies beyond the A images contribute zeros
+        const bool live = c < jb.a_total;
         const uint8_t* src = smem + stage * kStageBytes + c * kSubChunk + g * 8 * 16;
         float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (live) {
@@ -203,7 +249,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
       if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
     float* part = p.scratch + static_cast<size_t>(blockIdx.x) * kWgScratchFloats;
-    if (have && jb.bias && g == 0 && c < a_chunks) {
+    if (have && jb.bias && g == 0 && c < jb.a_total) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) part[65536 + c * 8 + q] = acc[q];
     }
@@ -212,15 +258,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     tc_fence_after_sync();
     if (have && warp >= 2 && warp < 6) {
       const int q4 = warp & 3;
-      for (int mh = 0; mh < m_halves; ++mh) {
-        const int m = mh * 128 + q4 * 32 + lane;
-        const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(q4) * 32u) << 16) + mh * 256;
-        for (int c0 = 0; c0 < jb.b_cols; c0 += 16) {
+      const int m = q4 * 32 + lane;
+      for (int s = 0; s < jb.n_sub; ++s) {
+        const Sub sb = jb.sub[s];
+        const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(q4) * 32u) << 16) + sb.tmem_col;
+        // scratch layout: NeRF jobs [(half*128 + m)][256]; bender jobs [sub][m][128]
+        float* dst_row = job_id <= 9 ? part + (s * 128 + m) * 256 : part + s * 16384 + m * 128;
+        for (int c0 = 0; c0 < sb.n; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
-          if (m < jb.a_cols && n_stages_total > 0) {
-            float4* dst = reinterpret_cast<float4*>(part + m * 256 + c0);
+          if (m < sb.a_cols && n_stages_total > 0) {
+            float4* dst = reinterpret_cast<float4*>(dst_row + c0);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
@@ -245,16 +294,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
 namespace {
 
 struct Src {
-  int job, m, n, n2;  // element (m, n) of job's partial; n2 >= 0: add a second column; n == -1: bias[m]
+  int job;   // job id
+  int off;   // float offset inside the job's partial (weights) or bias index (bias == 1)
+  int off2;  // second weight element to add (>= 0) or -1
+  int bias;
 };
+
+__device__ __forceinline__ Src nerf_w(int job, int m, int n) { return {job, m * 256 + n, -1, 0}; }
+__device__ __forceinline__ Src nerf_b(int job, int m) { return {job, m, -1, 1}; }
+__device__ __forceinline__ Src bend_w(int job, int sub, int m, int n, int n2 = -1) {
+  return {job, sub * 16384 + m * 128 + n, n2 >= 0 ? sub * 16384 + m * 128 + n2 : -1, 0};
+}
 
 __device__ __forceinline__ Src nerf_src(int idx, int out_ch, bool& ok) {
   ok = true;
-  // layers 0..7
   const int sz0 = 256 * 63 + 256, szl = 256 * 256 + 256, sz5 = 256 * 319 + 256;
   if (idx < sz0) {
-    if (idx < 256 * 63) return {9, idx / 63, idx % 63, -1};
-    return {9, idx - 256 * 63, -1, -1};
+    if (idx < 256 * 63) return nerf_w(9, idx / 63, idx % 63);
+    return nerf_b(9, idx - 256 * 63);
   }
   idx -= sz0;
   for (int l = 1; l < 8; ++l) {
@@ -263,59 +320,61 @@ __device__ __forceinline__ Src nerf_src(int idx, int out_ch, bool& ok) {
       if (l == 5) {
         if (idx < 256 * 319) {
           const int m = idx / 319, k = idx % 319;
-          return k < 63 ? Src{8, m, k, -1} : Src{5, m, k - 63, -1};
+          return k < 63 ? nerf_w(8, m, k) : nerf_w(5, m, k - 63);
         }
-        return {5, idx - 256 * 319, -1, -1};
+        return nerf_b(5, idx - 256 * 319);
       }
-      if (idx < 65536) return {l, idx >> 8, idx & 255, -1};
-      return {l, idx - 65536, -1, -1};
+      if (idx < 65536) return nerf_w(l, idx >> 8, idx & 255);
+      return nerf_b(l, idx - 65536);
     }
     idx -= sz;
   }
   if (idx < out_ch * 256) {
     const int m = idx >> 8;
     ok = m < 4;   // output channel 4 never reaches the loss: zero gradient
-    return {0, m, idx & 255, -1};
+    return nerf_w(0, m, idx & 255);
   }
   idx -= out_ch * 256;
   ok = idx < 4;
-  return {0, idx, -1, -1};
+  return nerf_b(0, idx);
 }
 
+// A-chunk layout of the bender jobs (bias index = column inside the concatenated A images):
+//   job 10: Yb4 cols 0-15 | Yb3 cols 16-79 | Yb2 cols 80-159      job 11: Yb1 cols 0-95 | Yb0 cols 96-191
 __device__ __forceinline__ Src bender_src(int idx, bool& ok) {
   ok = true;
   if (idx < 64 * 35) {  // net_w0: xyz columns collect the hi and lo operand columns
     const int m = idx / 35, k = idx % 35;
-    return k < 3 ? Src{14, m, k, k + 3} : Src{14, m, 6 + (k - 3), -1};
+    return k < 3 ? bend_w(11, 1, m, k, k + 3) : bend_w(11, 1, m, 6 + (k - 3));
   }
   idx -= 64 * 35;
-  if (idx < 64) return {14, idx, -1, -1};
+  if (idx < 64) return {11, 96 + idx, -1, 1};                                    // net_b0
   idx -= 64;
-  if (idx < 4096) return {13, idx >> 6, idx & 63, -1};
+  if (idx < 4096) return bend_w(11, 0, idx >> 6, idx & 63);                      // net_w1
   idx -= 4096;
-  if (idx < 64) return {13, idx, -1, -1};
+  if (idx < 64) return {11, idx, -1, 1};                                         // net_b1
   idx -= 64;
-  if (idx < 4096) return {12, idx >> 6, idx & 63, -1};
+  if (idx < 4096) return bend_w(10, 2, idx >> 6, idx & 63);                      // net_w2
   idx -= 4096;
-  if (idx < 64) return {12, idx, -1, -1};
+  if (idx < 64) return {10, 80 + idx, -1, 1};                                    // net_b2
   idx -= 64;
-  if (idx < 4096) return {11, idx >> 6, idx & 63, -1};
+  if (idx < 4096) return bend_w(10, 1, idx >> 6, idx & 63);                      // net_w3
   idx -= 4096;
-  if (idx < 64) return {11, idx, -1, -1};
+  if (idx < 64) return {10, 16 + idx, -1, 1};                                    // net_b3
   idx -= 64;
-  if (idx < 192) return {10, idx >> 6, idx & 63, -1};
+  if (idx < 192) return bend_w(10, 0, idx >> 6, idx & 63);                       // net_w4
   idx -= 192;
-  if (idx < 96) return {14, 64 + idx / 3, idx % 3, idx % 3 + 3};       // rig_w0
+  if (idx < 96) return bend_w(11, 1, 64 + idx / 3, idx % 3, idx % 3 + 3);        // rig_w0
   idx -= 96;
-  if (idx < 32) return {14, 64 + idx, -1, -1};                          // rig_b0
+  if (idx < 32) return {11, 96 + 64 + idx, -1, 1};                               // rig_b0
   idx -= 32;
-  if (idx < 1024) return {13, 64 + (idx >> 5), 64 + (idx & 31), -1};    // rig_w1
+  if (idx < 1024) return bend_w(11, 0, 64 + (idx >> 5), 64 + (idx & 31));        // rig_w1
   idx -= 1024;
-  if (idx < 32) return {13, 64 + idx, -1, -1};                          // rig_b1
+  if (idx < 32) return {11, 64 + idx, -1, 1};                                    // rig_b1
   idx -= 32;
-  if (idx < 32) return {12, 64, 64 + idx, -1};                          // rig_w2
+  if (idx < 32) return bend_w(10, 2, 64, 64 + idx);                              // rig_w2
   idx -= 32;
-  return {12, 64, -1, -1};                                               // rig_b2
+  return {10, 80 + 64, -1, 1};                                                   // rig_b2
 }
 
 }  // namespace
@@ -336,17 +395,23 @@ __global__ void wgrad_reduce_kernel(const WgradParams p, float* __restrict__ ner
     }
   }
   float sum = 0.f;
-  if (ok && s.job < p.n_jobs) {
-    int base = 0;
-    for (int j = 0; j < s.job; ++j) base += p.splits[j];
-    const int per = (p.n_tiles + p.splits[s.job] - 1) / p.splits[s.job];
-    for (int sp = 0; sp < p.splits[s.job]; ++sp) {
-      if (sp * per >= p.n_tiles) break;   // this split owned no tiles: its scratch is unwritten
-      const float* part = p.scratch + static_cast<size_t>(base + sp) * kWgScratchFloats;
-      if (s.n < 0) sum += part[65536 + s.m];
-      else {
-        sum += part[s.m * 256 + s.n];
-        if (s.n2 >= 0) sum += part[s.m * 256 + s.n2];
+  if (ok && !(s.bias && p.compact)) {
+    int base = 0, slot = -1;
+    for (int j = 0; j < p.n_jobs; ++j) {
+      if (p.job_ids[j] == s.job) { slot = j; break; }
+      base += p.splits[j];
+    }
+    if (slot >= 0) {
+      const int nsplit = p.splits[slot];
+      const int per = (p.n_tiles + nsplit - 1) / nsplit;
+      for (int sp = 0; sp < nsplit; ++sp) {
+        if (sp * per >= p.n_tiles) break;   // this split owned no tiles: its scratch is unwritten
+        const float* part = p.scratch + static_cast<size_t>(base + sp) * kWgScratchFloats;
+        if (s.bias) sum += part[65536 + s.off];
+        else {
+          sum += part[s.off];
+          if (s.off2 >= 0) sum += part[s.off2];
+        }
       }
     }
   }
@@ -357,23 +422,27 @@ __global__ void wgrad_reduce_kernel(const WgradParams p, float* __restrict__ ner
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, float* nerf_grad, int nerf_n, float* bend_grad,
                          int bend_n, int out_ch, cudaStream_t st) {
-  p.n_jobs = has_bender ? 15 : 10;
-  // bytes per tile of every job -> proportional split of the CTAs
-  static const int cols[15][2] = {{16, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256}, {256, 256},
-                                  {256, 64}, {256, 64},  {16, 64},   {64, 64},   {80, 96},   {96, 96},   {96, 48}};
+  // chunks (1 KB per 64-row stage) moved per stage by every job -> proportional split of the CTAs
+  static const int kJobChunks[12] = {2 + 32, 64, 64, 64, 64, 64, 64, 64, 32 + 8, 32 + 8, 20 + 28, 24 + 18};
+  int first = 0, last = has_bender ? 12 : 10;
+  if (p.compact) { first = 10; last = 12; p.stash_tile_bytes = kTanTileBytes; p.gstash_tile_bytes = kAdjTileBytes; }
+  else { p.stash_tile_bytes = kStashTileBytes; p.gstash_tile_bytes = kGradTileBytes; }
+  p.n_jobs = last - first;
   long long total = 0;
-  for (int j = 0; j < p.n_jobs; ++j) total += cols[j][0] + cols[j][1];
+  for (int j = first; j < last; ++j) total += kJobChunks[j];
   int used = 0;
-  for (int j = 0; j < p.n_jobs; ++j) {
-    int s = static_cast<int>((static_cast<long long>(num_sms) * (cols[j][0] + cols[j][1])) / total);
+  for (int j = first; j < last; ++j) {
+    int s = static_cast<int>((static_cast<long long>(num_sms) * kJobChunks[j]) / total);
     if (s < 1) s = 1;
     if (s > p.n_tiles) s = p.n_tiles > 0 ? p.n_tiles : 1;
-    p.splits[j] = s;
+    p.job_ids[j - first] = j;
+    p.splits[j - first] = s;
     used += s;
   }
-  // hand the remainder to the big jobs (L1..L7)
-  for (int j = 1; used < num_sms && p.n_tiles > 0; j = j % 7 + 1) {
-    if (p.splits[j] < p.n_tiles) { ++p.splits[j]; ++used; } else if (j == 7) break;
+  // hand the remainder to the biggest jobs, round robin
+  for (int guard = 0; used < num_sms && p.n_tiles > 0 && guard < 4 * num_sms; ++guard) {
+    const int j = p.compact ? guard % p.n_jobs : 1 + guard % 7;
+    if (p.splits[j] < p.n_tiles) { ++p.splits[j]; ++used; }
   }
   if (p.n_tiles > 0) {
     const size_t smem = kWgStages * kStageBytes + sizeof(Shared) + 64;
@@ -384,7 +453,7 @@ cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, float* ner
     if (e != cudaSuccess) return e;
   }
   const int n = nerf_n + bend_n;
-  wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, nerf_grad, nerf_n, bend_grad, bend_n, out_ch);
+  if (n > 0) wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, nerf_grad, nerf_n, bend_grad, bend_n, out_ch);
   return cudaGetLastError();
 }
 

@@ -14,7 +14,10 @@ struct WgradParams {
   float* scratch;          // [kWgMaxCtas][kWgScratchFloats]
   const float* amax;       // loss-scale source (see field_bwd.cu) or null
   int n_tiles;
+  int compact;             // 1: stashes hold only the bender images (divergence regulariser), bender jobs only
+  long long stash_tile_bytes, gstash_tile_bytes;   // filled in by launch_wgrad
   int n_jobs;
+  int job_ids[16];
   int splits[16];
   int* err;
 };

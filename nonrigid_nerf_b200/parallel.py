@@ -26,6 +26,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from . import autograd as _ag
 from . import run_nerf_helpers as H
 from . import train as T
 
@@ -238,12 +239,9 @@ class training_wrapper_class(torch.nn.Module):
             offsets_loss = offsets_loss + args.rigidity_loss_weight * torch.mean((w * rig).view(n_rays, -1), dim=-1)
             loss = loss + args.offsets_loss_weight * sched * offsets_loss
         if self.ray_bender is not None and args.divergence_loss_weight > 0.0:
-            pts = extras["initial_input_pts"].reshape(-1, 3)
-            lat = info["ray_bending_latents"]
-            lat = lat.view(n_rays, 1, -1).expand(n_rays, args.N_samples, lat.shape[-1]).reshape(-1, lat.shape[-1])
-            w = 1.0 - torch.exp(-F.relu(extras["opacity_alpha"].reshape(-1)))
-            div = H.compute_divergence_loss(extras["masked_offsets"].reshape(-1, 3), pts, lat, render_kwargs_train["ray_bender"],
-                                            exact=False, chunk=args.chunk, N_rays=n_rays, weights=w, backprop_into_weights=False)
+            # exact_divergence = False, backprop_into_weights = False (train.py:246-247); fused closed-form kernel
+            w = 1.0 - torch.exp(-F.relu(extras["opacity_alpha"].detach()))
+            div = _ag.divergence_loss(extras["unmasked_offsets"], extras["rigidity_mask"], w, self.ray_bender)
             loss = loss + args.divergence_loss_weight * sched * div
         return loss
 

@@ -186,3 +186,46 @@ def test_gradients_without_bender_and_ragged_batch():
             e = _rel(net.pts_linears[i].weight.grad.cpu(), po["pts_w"][i].grad)
             print(f"  layer {i} W: rel grad err {e:.3e}")
             assert e <= 6e-2, (i, e)
+
+
+def test_fused_divergence_regulariser_matches_oracle_double_backward():
+    """Closed-form divergence term (csrc/div.cu) vs the oracle's autograd.grad(create_graph=True) restatement of
+    run_nerf_helpers.py:22-116 / train.py:245-286, same probe vectors e: per-ray values and all gradients."""
+    from nonrigid_nerf_b200 import _lib, autograd as ag
+    seed, n = 611, 96
+    coarse, fine, bender, (cp, fp, bp) = helpers.build_models(O, seed, DEV)
+    r = O.make_rays(seed, n)
+    rnd = O.make_randomness(seed, n, 64, 64)
+    e = torch.randn(n * 64, 3, generator=torch.Generator().manual_seed(5))
+    lat = r["latents"].clone().to(DEV).requires_grad_(True)
+    rr = dict(r); rr["latents"] = lat
+    rgb, disp, acc, extras = _render(coarse, fine, bender, rr, perturb=1.0, noise=1.0, rnd=rnd)
+    w = 1.0 - torch.exp(-torch.relu(extras["opacity_alpha"].detach()))
+    div = ag.divergence_loss(extras["unmasked_offsets"], extras["rigidity_mask"], w, bender, e.to(DEV))
+    assert div.shape == (n,)
+    (div.mean() * 1e3).backward()
+    _lib.device_error_check()
+
+    cpo, fpo, bpo = O.clone_params(cp, True), O.clone_params(fp, True), O.clone_params(bp, True)
+    lat_o = r["latents"].clone().requires_grad_(True)
+    ret_o = O.render_rays(cpo, fpo, bpo, r["rays_o"], r["rays_d"], r["near"], r["far"], lat_o, 64, 64, perturb=True,
+                          raw_noise_std=1.0, rnd=rnd)
+    div_o = O.divergence_loss(bpo, ret_o, lat_o, n, 64, e)
+    (div_o.mean() * 1e3).backward()
+    rel_v = _rel(div.detach().cpu(), div_o.detach())
+    print(f"divergence loss per ray: rel err {rel_v:.3e} (mean {float(div_o.mean()):.3e})")
+    assert rel_v <= 2e-2
+    for i in range(5):
+        e_w = _rel(bender.network[i].weight.grad.cpu(), bpo["net_w"][i].grad)
+        print(f"  net {i} W: {e_w:.3e}")
+        assert e_w <= 8e-2, (i, e_w)
+        if i < 4:
+            assert _rel(bender.network[i].bias.grad.cpu(), bpo["net_b"][i].grad) <= 8e-2
+    for i in range(3):
+        e_w = _rel(bender.rigidity_network[i].weight.grad.cpu(), bpo["rig_w"][i].grad)
+        print(f"  rigidity {i} W: {e_w:.3e}")
+        assert e_w <= 8e-2, (i, e_w)
+        assert _rel(bender.rigidity_network[i].bias.grad.cpu(), bpo["rig_b"][i].grad) <= 8e-2
+    e_l = _rel(lat.grad.cpu(), lat_o.grad)
+    print(f"  latents: {e_l:.3e}")
+    assert e_l <= 8e-2
