@@ -74,11 +74,11 @@ struct Waiter {
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 
 // dY = dh * [h > 0]: drain NCOLS accumulator columns, mask with the forward activation stashed as
-// fp16 (row pointer `mask_row` into the stash tile), write fp16 to the next A operand (smem) and to
-// the gradient stash (global).
+// fp16 (row pointer `mask_row` into the stash tile), write fp16 to the next A operand (smem); the whole
+// image then goes to the gradient stash with a bulk TMA store (stash_store in the kernel body).
 template <int NCOLS>
 __device__ __forceinline__ void epi_mask_store(uint32_t taddr, const uint8_t* __restrict__ mask_row,
-                                               uint8_t* dst_row, uint8_t* g_row) {
+                                               uint8_t* dst_row) {
 #pragma unroll 1
   for (int c0 = 0; c0 < NCOLS; c0 += 32) {
     uint32_t v[32];
@@ -99,7 +99,6 @@ __device__ __forceinline__ void epi_mask_store(uint32_t taddr, const uint8_t* __
       }
       const uint4 pk = make_uint4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<uint4*>(dst_row + ((c0 >> 3) + q) * kChunkBytes) = pk;
-      *reinterpret_cast<uint4*>(g_row + ((c0 >> 3) + q) * kChunkBytes) = pk;
     }
   }
 }
@@ -287,7 +286,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
       const long long pt = tile * kTileM + row;
       const bool valid = pt < p.P;
       const uint8_t* st = p.stash + tile * kStashTileBytes + row * 16;
-      uint8_t* gs = p.gstash + tile * kGradTileBytes + row * 16;
+      uint8_t* gs = p.gstash + tile * kGradTileBytes;
+      uint8_t* a_img = act + slot * kHBytes;
+      const bool wg_leader = (threadIdx.x & 127) == 0;
+      // gradient stash: bulk TMA stores of finished images from shared memory (see field_fwd.cu)
+      auto stash_begin = [&]() {
+        if (wg_leader) tma_bulk_wait_read<0>();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+      };
+      auto stash_store = [&](uint32_t off, uint32_t bytes) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+        if (wg_leader) {
+          for (uint32_t o = 0; o < bytes; o += 16384u) tma_bulk_s2g(gs + off + o, a_img + o, bytes - o < 16384u ? bytes - o : 16384u);
+          tma_bulk_commit();
+        }
+      };
 
       // ---- d_raw image: [g_r g_g g_b g_sigma 0 ...] (K = 16) ----
       {
@@ -299,10 +313,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         }
         const uint4 c0 = make_uint4(pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), 0u, 0u);
         const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
+        stash_begin();
         *reinterpret_cast<uint4*>(a_row) = c0;
         *reinterpret_cast<uint4*>(a_row + kChunkBytes) = zz;
-        *reinterpret_cast<uint4*>(gs + kGsRaw) = c0;
-        *reinterpret_cast<uint4*>(gs + kGsRaw + kChunkBytes) = zz;
+        stash_store(kGsRaw, 2 * kChunkBytes);
       }
       signal_ready();
       float dx[3] = {0.f, 0.f, 0.f};
@@ -310,7 +324,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
 #pragma unroll 1
       for (int s = 0; s < 3; ++s) {
         wait_acc(300 + s);
-        epi_mask_store<256>(taddr, st + kStH + (7 - s) * kHBytes, a_row, gs + kGsY + (7 - s) * kHBytes);
+        stash_begin();
+        epi_mask_store<256>(taddr, st + kStH + (7 - s) * kHBytes, a_row);
+        stash_store(kGsY + (7 - s) * kHBytes, kHBytes);
         signal_ready();
       }
       // ---- L5e^T: gradient into the skip-connected embedding ----
@@ -321,7 +337,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
 #pragma unroll 1
       for (int s = 0; s < 5; ++s) {
         wait_acc(304 + s);
-        epi_mask_store<256>(taddr, st + kStH + (4 - s) * kHBytes, a_row, gs + kGsY + (4 - s) * kHBytes);
+        stash_begin();
+        epi_mask_store<256>(taddr, st + kStH + (4 - s) * kHBytes, a_row);
+        stash_store(kGsY + (4 - s) * kHBytes, kHBytes);
         signal_ready();
       }
       // ---- L0^T: gradient into the embedding; then through the bend ----
@@ -356,34 +374,40 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         if (!valid) { dun[0] = dun[1] = dun[2] = 0.f; drpre = 0.f; }
         const uint4 c0 = make_uint4(pack_h2(clamp_h(dun[0]), clamp_h(dun[1])), pack_h2(clamp_h(dun[2]), 0.f), 0u, 0u);
         const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
+        stash_begin();
         *reinterpret_cast<uint4*>(a_row) = c0;
         *reinterpret_cast<uint4*>(a_row + kChunkBytes) = zz;
-        *reinterpret_cast<uint4*>(gs + kGsYb4) = c0;
-        *reinterpret_cast<uint4*>(gs + kGsYb4 + kChunkBytes) = zz;
+        stash_store(kGsYb4, 2 * kChunkBytes);
       }
       signal_ready();
       // ---- B4^T -> dYb3 ----
       wait_acc(310);
-      epi_mask_store<64>(taddr, st + kStHb4, a_row, gs + kGsYb3);
+      stash_begin();
+      epi_mask_store<64>(taddr, st + kStHb4, a_row);
+      stash_store(kGsYb3, 8 * kChunkBytes);
       signal_ready();
       // ---- B3^T -> dYb2 = [dh * mask (64) | d rigidity pre-activation | 0 (15)] ----
       wait_acc(311);
-      epi_mask_store<64>(taddr, st + kStHb3, a_row, gs + kGsYb2);
+      stash_begin();
+      epi_mask_store<64>(taddr, st + kStHb3, a_row);
       {
         const uint4 c8 = make_uint4(pack_h2(clamp_h(drpre), 0.f), 0u, 0u, 0u);
         const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(a_row + 8 * kChunkBytes) = c8;
         *reinterpret_cast<uint4*>(a_row + 9 * kChunkBytes) = zz;
-        *reinterpret_cast<uint4*>(gs + kGsYb2 + 8 * kChunkBytes) = c8;
-        *reinterpret_cast<uint4*>(gs + kGsYb2 + 9 * kChunkBytes) = zz;
       }
+      stash_store(kGsYb2, 10 * kChunkBytes);
       signal_ready();
       // ---- B2^T -> dYb1, B1^T -> dYb0 ----
       wait_acc(312);
-      epi_mask_store<96>(taddr, st + kStHb2, a_row, gs + kGsYb1);
+      stash_begin();
+      epi_mask_store<96>(taddr, st + kStHb2, a_row);
+      stash_store(kGsYb1, 12 * kChunkBytes);
       signal_ready();
       wait_acc(313);
-      epi_mask_store<96>(taddr, st + kStHb1, a_row, gs + kGsYb0);
+      stash_begin();
+      epi_mask_store<96>(taddr, st + kStHb1, a_row);
+      stash_store(kGsYb0, 12 * kChunkBytes);
       signal_ready();
       // ---- B0^T: d(bender input); columns 6..37 are the latent code -> per-ray reduction ----
       wait_acc(314);
@@ -412,6 +436,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
       }
       // next a_ready arrival: the next pair's d_raw image
     }
+    if ((threadIdx.x & 127) == 0) tma_bulk_wait<0>();   // all gradient-stash stores complete before the CTA exits
   }
 
   tc_fence_before_sync();

@@ -87,7 +87,7 @@ __device__ __forceinline__ float relu_h(float v) { return fminf(fmaxf(v, 0.f), 6
 // as chunks [chunk0, chunk0 + NCOLS/8) of this thread's row in a chunk-major activation image.
 template <int NCOLS>
 __device__ __forceinline__ void epi_bias_relu_store(uint32_t taddr, const float* __restrict__ bias,
-                                                    uint8_t* dst_row, uint8_t* stash_row) {
+                                                    uint8_t* dst_row) {
 #pragma unroll 1
   for (int c0 = 0; c0 < NCOLS; c0 += 32) {
     uint32_t v[32];
@@ -103,7 +103,6 @@ __device__ __forceinline__ void epi_bias_relu_store(uint32_t taddr, const float*
       pk.z = pack_h2(relu_h(__uint_as_float(v[q * 8 + 4]) + b1.x), relu_h(__uint_as_float(v[q * 8 + 5]) + b1.y));
       pk.w = pack_h2(relu_h(__uint_as_float(v[q * 8 + 6]) + b1.z), relu_h(__uint_as_float(v[q * 8 + 7]) + b1.w));
       *reinterpret_cast<uint4*>(dst_row + ((c0 >> 3) + q) * kChunkBytes) = pk;
-      if (stash_row) *reinterpret_cast<uint4*>(stash_row + ((c0 >> 3) + q) * kChunkBytes) = pk;  // training stash
     }
   }
 }
@@ -113,7 +112,7 @@ __device__ __forceinline__ void epi_bias_relu_store(uint32_t taddr, const float*
 // Written as fp16 chunks 0..7 of the row (63 features + one zero pad column).
 // sin/cos: the argument 2^k * x is reduced EXACTLY to [-0.5, 0.5) turns (x / 2pi carried as a
 // two-float value), then evaluated with MUFU (abs err ~4e-7), well below fp16 resolution.
-__device__ __forceinline__ void write_pe(const float (&x)[3], uint8_t* dst_row, uint8_t* stash_row) {
+__device__ __forceinline__ void write_pe(const float (&x)[3], uint8_t* dst_row) {
   float f[64];
   f[0] = x[0]; f[1] = x[1]; f[2] = x[2];
   const float kInv2PiHi = 0.15915494f;      // fl(1/2pi)
@@ -141,7 +140,6 @@ __device__ __forceinline__ void write_pe(const float (&x)[3], uint8_t* dst_row, 
     pk.z = pack_h2(f[c * 8 + 4], f[c * 8 + 5]);
     pk.w = pack_h2(f[c * 8 + 6], f[c * 8 + 7]);
     *reinterpret_cast<uint4*>(dst_row + c * kChunkBytes) = pk;
-    if (stash_row) *reinterpret_cast<uint4*>(stash_row + c * kChunkBytes) = pk;
   }
 }
 
@@ -265,8 +263,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const long long pt = (static_cast<long long>(pair) * 2 + slot) * kTileM + row;
       const bool valid = pt < p.P;
-      // training stash: this tile's block, this thread's row (invalid rows are stashed too: zeros downstream)
-      uint8_t* st = p.stash ? p.stash + (static_cast<long long>(pair) * 2 + slot) * kStashTileBytes + row * 16 : nullptr;
+      // Training stash: every finished activation image (a contiguous chunk-major block of shared memory) is
+      // written to this tile's stash block with bulk TMA stores issued by one thread of the warpgroup; the
+      // epilogue threads spend no load/store slots on it.  stash_begin(): the previous store must have finished
+      // READING shared memory before any image is overwritten.
+      uint8_t* st = p.stash ? p.stash + (static_cast<long long>(pair) * 2 + slot) * kStashTileBytes : nullptr;
+      const bool wg_leader = (threadIdx.x & 127) == 0;
+      auto stash_begin = [&]() {
+        if (st) {
+          if (wg_leader) tma_bulk_wait_read<0>();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+        }
+      };
+      auto stash_store = [&](uint32_t stash_off, const uint8_t* img, uint32_t bytes) {
+        if (st) {
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+          if (wg_leader) {
+            for (uint32_t o = 0; o < bytes; o += 16384u) tma_bulk_s2g(st + stash_off + o, img + o, bytes - o < 16384u ? bytes - o : 16384u);
+            tma_bulk_commit();
+          }
+        }
+      };
       float x[3] = {0.f, 0.f, 0.f};
       long long ray = 0;
       if (valid) {
@@ -289,6 +307,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
       float rigidity = 0.f;
       if (HAS_BENDER) {
         // ---- bender input row: [xyz_hi(3) xyz_lo(3) latent(32) 0(10)] fp16, chunks 0..5 of E ----
+        stash_begin();
         float in[48];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
@@ -309,19 +328,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           pk.z = pack_h2(in[c * 8 + 4], in[c * 8 + 5]);
           pk.w = pack_h2(in[c * 8 + 6], in[c * 8 + 7]);
           *reinterpret_cast<uint4*>(e_row + c * kChunkBytes) = pk;
-          if (st) *reinterpret_cast<uint4*>(st + kStBin + c * kChunkBytes) = pk;
         }
+        stash_store(kStBin, Es, 6 * kChunkBytes);
         signal_ready();
         // ---- B0, B1: 96 hidden units (64 offset | 32 rigidity) ----
         wait_acc(301);
-        epi_bias_relu_store<96>(taddr, p.bend_bias, h_row, st ? st + kStHb1 : nullptr);
+        stash_begin();
+        epi_bias_relu_store<96>(taddr, p.bend_bias, h_row);
+        stash_store(kStHb1, Hs, 12 * kChunkBytes);
         signal_ready();
         wait_acc(302);
-        epi_bias_relu_store<96>(taddr, p.bend_bias + 96, h_row, st ? st + kStHb2 : nullptr);
+        stash_begin();
+        epi_bias_relu_store<96>(taddr, p.bend_bias + 96, h_row);
+        stash_store(kStHb2, Hs, 12 * kChunkBytes);
         signal_ready();
         // ---- B2: 64 offset hidden + rigidity output (column 64) ----
         wait_acc(303);
-        epi_bias_relu_store<64>(taddr, p.bend_bias + 192, h_row, st ? st + kStHb3 : nullptr);
+        stash_begin();
+        epi_bias_relu_store<64>(taddr, p.bend_bias + 192, h_row);
+        stash_store(kStHb3, Hs, 8 * kChunkBytes);
         {
           uint32_t v[16];
           tmem_ld16(taddr + 64, v);
@@ -333,7 +358,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
         signal_ready();
         // ---- B3 ----
         wait_acc(304);
-        epi_bias_relu_store<64>(taddr, p.bend_bias + 272, h_row, st ? st + kStHb4 : nullptr);
+        stash_begin();
+        epi_bias_relu_store<64>(taddr, p.bend_bias + 272, h_row);
+        stash_store(kStHb4, Hs, 8 * kChunkBytes);
         signal_ready();
         // ---- B4: offsets; bend; positional encoding of the bent point -> E ----
         wait_acc(305);
@@ -360,13 +387,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
       if (valid && p.d_bent) {
         p.d_bent[pt * 3 + 0] = x[0]; p.d_bent[pt * 3 + 1] = x[1]; p.d_bent[pt * 3 + 2] = x[2];
       }
-      write_pe(x, e_row, st ? st + kStE : nullptr);
+      stash_begin();
+      write_pe(x, e_row);
+      stash_store(kStE, Es, kEBytes);
       signal_ready();
       // ---- L0 .. L7 ----
 #pragma unroll 1
       for (int L = 0; L < 8; ++L) {
         wait_acc(310 + L);
-        epi_bias_relu_store<256>(taddr, p.nerf_bias + L * 256, h_row, st ? st + kStH + L * kHBytes : nullptr);
+        stash_begin();
+        epi_bias_relu_store<256>(taddr, p.nerf_bias + L * 256, h_row);
+        stash_store(kStH + L * kHBytes, Hs, kHBytes);
         signal_ready();
       }
       // ---- head: raw = output_linear(h) (run_nerf_helpers.py:306) ----
@@ -387,6 +418,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
       }
       // the next a_ready arrival is the next pair's prologue (which also means TMEM is drained)
     }
+    if (p.stash && (threadIdx.x & 127) == 0) tma_bulk_wait<0>();   // all stash stores complete before the CTA exits
   }
 
   tc_fence_before_sync();
