@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "../../include/nrnerf_b200.h"
 #include "nrn_common.cuh"
 #include "pack.cuh"
@@ -194,6 +195,7 @@ int nrn_field_forward(const NrnFieldArgs* a) {
   p.raw = a->raw; p.d_init = a->initial_input_pts; p.d_bent = a->input_pts; p.d_unmasked = a->unmasked_offsets;
   p.d_masked = a->masked_offsets; p.d_rigid = a->rigidity_mask;
   p.stash = static_cast<uint8_t*>(a->stash);
+  { const char* dm = getenv("NRN_DEBUG_MODE"); p.debug_mode = dm ? atoi(dm) : 0; }
   if (a->stash && a->points) return fail(NRN_E_INVALID, "nrn_field_forward: the training stash needs ray mode");
   p.err = ds->err_word;
   cudaError_t e; { ScopedTimer tm(0, static_cast<cudaStream_t>(a->stream)); e = nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream)); }

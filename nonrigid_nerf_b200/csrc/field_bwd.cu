@@ -79,26 +79,31 @@ __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504
 template <int NCOLS>
 __device__ __forceinline__ void epi_mask_store(uint32_t taddr, const uint8_t* __restrict__ mask_row,
                                                uint8_t* dst_row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < NCOLS; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(taddr + c0, v);
+  // software pipeline: TMEM load of chunk c+1 and mask loads of chunk c overlap the processing
+  constexpr int NC = NCOLS / 32;
+  uint32_t v[2][32];
+  tmem_ld32(taddr, v[0]);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
     uint4 m[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) m[q] = __ldg(reinterpret_cast<const uint4*>(mask_row + ((c0 >> 3) + q) * kChunkBytes));
+    for (int q = 0; q < 4; ++q) m[q] = __ldg(reinterpret_cast<const uint4*>(mask_row + (c * 4 + q) * kChunkBytes));
     tmem_ld_wait();
+    if (c + 1 < NC) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+    const uint32_t(&w)[32] = v[c & 1];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const uint32_t mw[4] = {m[q].x, m[q].y, m[q].z, m[q].w};
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float a = (mw[j] & 0x7fffu) ? clamp_h(__uint_as_float(v[q * 8 + 2 * j])) : 0.f;
-        const float b = (mw[j] & 0x7fff0000u) ? clamp_h(__uint_as_float(v[q * 8 + 2 * j + 1])) : 0.f;
-        o[j] = pack_h2(a, b);
+        // dY = dh * [h > 0] on packed halves: saturating convert, then multiply by the 0/1 mask of the stashed h
+        const uint32_t g2 = pack_h2_sat(__uint_as_float(w[q * 8 + 2 * j]), __uint_as_float(w[q * 8 + 2 * j + 1]));
+        const __half2 hm = __hgt2(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
+        const __half2 r2 = __hmul2(*reinterpret_cast<const __half2*>(&g2), hm);
+        o[j] = *reinterpret_cast<const uint32_t*>(&r2);
       }
-      const uint4 pk = make_uint4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<uint4*>(dst_row + ((c0 >> 3) + q) * kChunkBytes) = pk;
+      *reinterpret_cast<uint4*>(dst_row + (c * 4 + q) * kChunkBytes) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         for (int step = 0; step < kNumSteps; ++step) {
           const StepShape s = step_shape(step);
           const uint8_t* src = step < 10 ? p.nerf_wT + gn : p.bend_wT + gb;
-          for (int slot = 0; slot < 2; ++slot) {
+          {   // one copy per step: both slots consume the same slab (lock-step schedule)
             for (uint32_t j = 0; j < s.nslabs; ++j) {
               W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
               uint8_t* dst = ring + stage * kRingStageBytes;
@@ -229,25 +234,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         for (int step = 0; step < kNumSteps; ++step) {
           const StepShape s = step_shape(step);
           const uint32_t idesc = umma_instr_desc(kTileM, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
-          for (int slot = 0; slot < 2; ++slot) {
-            W.wait(&sh->a_ready[slot], aph[slot], 201);
-            aph[slot] ^= 1u;
+          // Lock-step schedule: every weight slab is used for BOTH slots before it is released, which halves the
+          // L2 -> shared-memory weight traffic (the limiter of the one-slab-per-slot schedule: 63 GB per 8.4 M points).
+          for (uint32_t j = 0; j < s.nslabs; ++j) {
+            W.wait(&sh->w_full[stage], phase, 202);
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            const uint32_t a_base = smem_u32(act + slot * kHBytes);
-            for (uint32_t j = 0; j < s.nslabs; ++j) {
-              W.wait(&sh->w_full[stage], phase, 202);
-              tc_fence_after_sync();
-              const uint64_t adesc = umma_smem_desc(a_base + j * 8 * kChunkBytes, kChunkBytes, 128);
-              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
+            const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
+            for (int slot = 0; slot < 2; ++slot) {
+              if (j == 0) {
+                W.wait(&sh->a_ready[slot], aph[slot], 201);
+                aph[slot] ^= 1u;
+                tc_fence_after_sync();
+              }
+              const uint32_t d_tmem = tmem_base + slot * 256;
+              const uint64_t adesc = umma_smem_desc(smem_u32(act + slot * kHBytes) + j * 8 * kChunkBytes, kChunkBytes, 128);
               for (uint32_t k = 0; k < s.k16; ++k) {
                 umma_f16_ss(d_tmem, umma_desc_advance(adesc, k * 2 * kChunkBytes),
                             umma_desc_advance(bdesc, k * 2 * s.N * 16), idesc, (j | k) ? 1u : 0u);
               }
-              umma_commit(&sh->w_empty[stage]);
-              if (++stage == kBwdRingStages) { stage = 0; phase ^= 1u; }
+              if (j + 1 == s.nslabs) umma_commit(&sh->d_full[slot]);   // this slot's accumulator is complete
             }
-            umma_commit(&sh->d_full[slot]);
+            umma_commit(&sh->w_empty[stage]);                          // slab free once both slots' MMAs retire
+            if (++stage == kBwdRingStages) { stage = 0; phase ^= 1u; }
           }
         }
       }

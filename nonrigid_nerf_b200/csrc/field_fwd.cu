@@ -88,21 +88,29 @@ __device__ __forceinline__ float relu_h(float v) { return fminf(fmaxf(v, 0.f), 6
 template <int NCOLS>
 __device__ __forceinline__ void epi_bias_relu_store(uint32_t taddr, const float* __restrict__ bias,
                                                     uint8_t* dst_row) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < NCOLS; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(taddr + c0, v);
+  // software pipeline: the TMEM load of chunk c+1 and the bias loads of chunk c are in flight while
+  // chunk c-1 / c is being processed (tcgen05.wait::ld only ever waits for a load issued a block ago)
+  constexpr int NC = NCOLS / 32;
+  uint32_t v[2][32];
+  tmem_ld32(taddr, v[0]);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float4 b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + i * 4));
     tmem_ld_wait();
+    if (c + 1 < NC) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+    const uint32_t(&w)[32] = v[c & 1];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + q * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + q * 8 + 4));
+      const float4 b0 = b[2 * q], b1 = b[2 * q + 1];
       uint4 pk;
-      pk.x = pack_h2(relu_h(__uint_as_float(v[q * 8 + 0]) + b0.x), relu_h(__uint_as_float(v[q * 8 + 1]) + b0.y));
-      pk.y = pack_h2(relu_h(__uint_as_float(v[q * 8 + 2]) + b0.z), relu_h(__uint_as_float(v[q * 8 + 3]) + b0.w));
-      pk.z = pack_h2(relu_h(__uint_as_float(v[q * 8 + 4]) + b1.x), relu_h(__uint_as_float(v[q * 8 + 5]) + b1.y));
-      pk.w = pack_h2(relu_h(__uint_as_float(v[q * 8 + 6]) + b1.z), relu_h(__uint_as_float(v[q * 8 + 7]) + b1.w));
-      *reinterpret_cast<uint4*>(dst_row + ((c0 >> 3) + q) * kChunkBytes) = pk;
+      // one cvt.rn.relu.satfinite.f16x2 per two outputs: ReLU, clamp to fp16 range and pack in a single instruction
+      pk.x = pack_h2_relu_sat(__uint_as_float(w[q * 8 + 0]) + b0.x, __uint_as_float(w[q * 8 + 1]) + b0.y);
+      pk.y = pack_h2_relu_sat(__uint_as_float(w[q * 8 + 2]) + b0.z, __uint_as_float(w[q * 8 + 3]) + b0.w);
+      pk.z = pack_h2_relu_sat(__uint_as_float(w[q * 8 + 4]) + b1.x, __uint_as_float(w[q * 8 + 5]) + b1.y);
+      pk.w = pack_h2_relu_sat(__uint_as_float(w[q * 8 + 6]) + b1.z, __uint_as_float(w[q * 8 + 7]) + b1.w);
+      *reinterpret_cast<uint4*>(dst_row + (c * 4 + q) * kChunkBytes) = pk;
     }
   }
 }
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
         for (int step = kFirstStep; step < 14; ++step) {
           const StepShape s = step_shape(step);
           const uint8_t* src = step < 5 ? p.bend_w + gb : p.nerf_w + gn;
-          for (int slot = 0; slot < 2; ++slot) {
+          {   // one copy per step: both slots consume the same slab (lock-step schedule)
             for (uint32_t j = 0; j < s.nslabs; ++j) {
               W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
               uint8_t* dst = ring + stage * kRingStageBytes;
@@ -216,25 +224,28 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
         for (int step = kFirstStep; step < 14; ++step) {
           const StepShape s = step_shape(step);
           const uint32_t idesc = umma_instr_desc(kTileM, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
-          for (int slot = 0; slot < 2; ++slot) {
-            W.wait(&sh->a_ready[slot], aph[slot], 201);
-            aph[slot] ^= 1u;
+          // Lock-step schedule: every weight slab is used for BOTH slots before it is released, which halves the
+          // L2 -> shared-memory weight traffic (the limiter of the one-slab-per-slot schedule: 63 GB per 8.4 M points).
+          for (uint32_t j = 0; j < s.nslabs; ++j) {
+            W.wait(&sh->w_full[stage], phase, 202);
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            const uint32_t a_base = smem_u32(act + slot * kSlotBytes);
-            for (uint32_t j = 0; j < s.nslabs; ++j) {
-              W.wait(&sh->w_full[stage], phase, 202);
-              tc_fence_after_sync();
-              const uint64_t adesc = umma_smem_desc(a_base + a_operand_offset(step, j), kChunkBytes, 128);
-              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
-              for (uint32_t k = 0; k < s.k16; ++k) {
+            const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
+            for (int slot = 0; slot < 2; ++slot) {
+              if (j == 0) {
+                W.wait(&sh->a_ready[slot], aph[slot], 201);
+                aph[slot] ^= 1u;
+                tc_fence_after_sync();
+              }
+              const uint32_t d_tmem = tmem_base + slot * 256;
+              const uint64_t adesc = umma_smem_desc(smem_u32(act + slot * kSlotBytes) + a_operand_offset(step, j), kChunkBytes, 128);
+              for (uint32_t k = 0; k < s.k16 && p.debug_mode != 2; ++k) {
                 umma_f16_ss(d_tmem, umma_desc_advance(adesc, k * 2 * kChunkBytes),
                             umma_desc_advance(bdesc, k * 2 * s.N * 16), idesc, (j | k) ? 1u : 0u);
               }
-              umma_commit(&sh->w_empty[stage]);  // slab free once these MMAs retire
-              if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
+              if (j + 1 == s.nslabs) umma_commit(&sh->d_full[slot]);   // this slot's accumulator is complete
             }
-            umma_commit(&sh->d_full[slot]);      // accumulator complete
+            umma_commit(&sh->w_empty[stage]);                          // slab free once both slots' MMAs retire
+            if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -396,7 +407,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
       for (int L = 0; L < 8; ++L) {
         wait_acc(310 + L);
         stash_begin();
-        epi_bias_relu_store<256>(taddr, p.nerf_bias + L * 256, h_row);
+        if (p.debug_mode != 1) epi_bias_relu_store<256>(taddr, p.nerf_bias + L * 256, h_row);
         stash_store(kStH + L * kHBytes, Hs, kHBytes);
         signal_ready();
       }

@@ -237,6 +237,18 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// {lo = relu(a), hi = relu(b)} as fp16x2, saturating to +-65504: bias-add results -> next layer's operand
+__device__ __forceinline__ uint32_t pack_h2_relu_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// {lo = a, hi = b} as fp16x2, saturating to +-65504
+__device__ __forceinline__ uint32_t pack_h2_sat(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
