@@ -195,7 +195,7 @@ def main():
     n_images = 86
     latents = [torch.zeros(32, device=dev).normal_(0, 0.1).requires_grad_(True) for _ in range(n_images)]
     grad_vars = latents + list(bender.parameters()) + list(coarse.parameters()) + list(fine.parameters())
-    optimizer = torch.optim.Adam(params=grad_vars, lr=5e-4, betas=(0.9, 0.999), capturable=not args.no_graph)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=5e-4, betas=(0.9, 0.999), capturable=not args.no_graph, fused=True)  # same Adam as train.py:656-658, PyTorch's fused kernel
     render_kwargs_train = {"network_query_fn": None, "perturb": 1.0, "N_importance": N_IMPORTANCE, "network_fine": fine,
                            "N_samples": N_SAMPLES, "network_fn": coarse, "ray_bender": bender, "use_viewdirs": False,
                            "white_bkgd": False, "raw_noise_std": 1.0, "ndc": False, "lindisp": False, "near": 0.0022, "far": 1.0024}

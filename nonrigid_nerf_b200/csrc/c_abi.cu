@@ -50,6 +50,7 @@ int device_state(DeviceState** out) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
     if (prop.major != 10) return fail(NRN_E_INVALID, "nrnerf_b200 needs an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
     s.num_sms = prop.multiProcessorCount;
+    if (const char* g = getenv("NRN_GRID")) { const int v = atoi(g); if (v > 0 && v < s.num_sms) s.num_sms = v; }   // developer experiments
     e = cudaMalloc(&s.err_word, 4 * sizeof(int));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(err word)");
     e = cudaMemset(s.err_word, 0, 4 * sizeof(int));

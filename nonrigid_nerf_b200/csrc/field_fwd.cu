@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
         for (int step = kFirstStep; step < 14; ++step) {
           const StepShape s = step_shape(step);
           const uint8_t* src = step < 5 ? p.bend_w + gb : p.nerf_w + gn;
-          {   // one copy per step: both slots consume the same slab (lock-step schedule)
+          for (int slot = 0; slot < 2; ++slot) {
             for (uint32_t j = 0; j < s.nslabs; ++j) {
               W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
               uint8_t* dst = ring + stage * kRingStageBytes;
@@ -224,28 +224,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
         for (int step = kFirstStep; step < 14; ++step) {
           const StepShape s = step_shape(step);
           const uint32_t idesc = umma_instr_desc(kTileM, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
-          // Lock-step schedule: every weight slab is used for BOTH slots before it is released, which halves the
-          // L2 -> shared-memory weight traffic (the limiter of the one-slab-per-slot schedule: 63 GB per 8.4 M points).
-          for (uint32_t j = 0; j < s.nslabs; ++j) {
-            W.wait(&sh->w_full[stage], phase, 202);
+          for (int slot = 0; slot < 2; ++slot) {
+            W.wait(&sh->a_ready[slot], aph[slot], 201);
+            aph[slot] ^= 1u;
             tc_fence_after_sync();
-            const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
-            for (int slot = 0; slot < 2; ++slot) {
-              if (j == 0) {
-                W.wait(&sh->a_ready[slot], aph[slot], 201);
-                aph[slot] ^= 1u;
-                tc_fence_after_sync();
-              }
-              const uint32_t d_tmem = tmem_base + slot * 256;
-              const uint64_t adesc = umma_smem_desc(smem_u32(act + slot * kSlotBytes) + a_operand_offset(step, j), kChunkBytes, 128);
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            const uint32_t a_base = smem_u32(act + slot * kSlotBytes);
+            for (uint32_t j = 0; j < s.nslabs; ++j) {
+              W.wait(&sh->w_full[stage], phase, 202);
+              tc_fence_after_sync();
+              const uint64_t adesc = umma_smem_desc(a_base + a_operand_offset(step, j), kChunkBytes, 128);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
               for (uint32_t k = 0; k < s.k16 && p.debug_mode != 2; ++k) {
                 umma_f16_ss(d_tmem, umma_desc_advance(adesc, k * 2 * kChunkBytes),
                             umma_desc_advance(bdesc, k * 2 * s.N * 16), idesc, (j | k) ? 1u : 0u);
               }
-              if (j + 1 == s.nslabs) umma_commit(&sh->d_full[slot]);   // this slot's accumulator is complete
+              umma_commit(&sh->w_empty[stage]);  // slab free once these MMAs retire
+              if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
             }
-            umma_commit(&sh->w_empty[stage]);                          // slab free once both slots' MMAs retire
-            if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
+            umma_commit(&sh->d_full[slot]);      // accumulator complete
           }
         }
       }
