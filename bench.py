@@ -215,22 +215,47 @@ def main():
         loss = torch.mean(losses)
         optimizer.zero_grad(set_to_none=True)
         loss.backward()
-        optimizer.step()
+        optimizer.step()          # world > 1: the pre-step hook all-reduces the gradients (one flat NCCL call)
         return loss
 
-    # the whole iteration (forward, losses, backward, all-reduce, Adam) is captured once and replayed
+    # CUDA-graph replay.  1 GPU: the whole iteration (forward, losses, backward, Adam) is one graph.
+    # N GPUs: the graph holds this rank's forward + backward only; the collectives (input broadcast, ONE flat
+    # gradient all-reduce, loss all-gather) and Adam run eagerly around it -- NCCL calls are not captured.
     graphed = None
+    lo, hi = parallel.shard_bounds(n_global, world, rank)
     if not args.no_graph:
         try:
             from nonrigid_nerf_b200.graphs import GraphedStep
-            graphed = GraphedStep(eager_step, resident[0], warmup=3)
+            if world == 1:
+                graphed = GraphedStep(eager_step, resident[0], warmup=3)
+            else:
+                parallel.UNIFORM_GRADS = True
+                local_module = train_fn.module   # training_wrapper_class: the per-rank step DataParallel used to wrap
+
+                def local_fwd_bwd(rays_o, rays_d, target, idx):
+                    losses = local_module(targs, rays_o, rays_d, 100, render_kwargs_train, target, 1000, 0, dataset_extras, idx)
+                    optimizer.zero_grad(set_to_none=True)
+                    (losses.sum() / n_global).backward()      # the caller's mean over the GLOBAL batch (train.py:1606-1607)
+                    return losses
+
+                graphed = GraphedStep(local_fwd_bwd, [t[lo:hi].contiguous() for t in resident[0]], warmup=3)
         except Exception as exc:  # noqa: BLE001 - fall back to the eager loop, and say so in the JSON line
             print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
             graphed = None
             torch.cuda.synchronize()
 
     def step(i, batch):
-        return graphed(*batch) if graphed is not None else eager_step(*batch)
+        if graphed is None:
+            return eager_step(*batch)
+        if world == 1:
+            return graphed(*batch)
+        for t in batch:                       # every rank uses rank 0's batch (the reference samples with unseeded numpy)
+            dist.broadcast(t, src=0)
+        losses_local = graphed(*[t[lo:hi] for t in batch])
+        optimizer.step()                      # pre-step hook: one flat gradient all-reduce, then Adam on every rank
+        gathered = torch.empty(world * (hi - lo), dtype=losses_local.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, losses_local.contiguous())   # per-ray losses [N_rand] on every rank
+        return gathered.mean()
 
     def barrier():
         if world > 1:
@@ -263,7 +288,10 @@ def main():
     if graphed is not None:
         # re-capture with the per-kernel event records inside the graph (external event-record nodes)
         _lib.timing_enable(True)
-        graphed = GraphedStep(eager_step, resident[0], warmup=1)
+        if world == 1:
+            graphed = GraphedStep(eager_step, resident[0], warmup=1)
+        else:
+            graphed = GraphedStep(local_fwd_bwd, [t[lo:hi].contiguous() for t in resident[0]], warmup=1)
         for i in range(3):
             step(i, resident[i % pool])
     else:

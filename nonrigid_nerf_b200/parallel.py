@@ -50,14 +50,18 @@ def shard_bounds(n: int, world: int, rank: int):
 
 
 def _map_tensors(obj: Any, fn: Callable[[torch.Tensor], Any]) -> Any:
+    """Apply fn to every tensor nested in dicts / lists / tuples.  Containers without tensors are returned
+    as the SAME object (DataParallel passes non-tensor arguments by reference)."""
     if isinstance(obj, torch.Tensor):
         return fn(obj)
     if isinstance(obj, dict):
-        return {k: _map_tensors(v, fn) for k, v in obj.items()}
-    if isinstance(obj, tuple):
-        return tuple(_map_tensors(v, fn) for v in obj)
-    if isinstance(obj, list):
-        return [_map_tensors(v, fn) for v in obj]
+        new = {k: _map_tensors(v, fn) for k, v in obj.items()}
+        return obj if all(new[k] is obj[k] for k in obj) else new
+    if isinstance(obj, (tuple, list)):
+        new = [_map_tensors(v, fn) for v in obj]
+        if all(a is b for a, b in zip(new, obj)):
+            return obj
+        return tuple(new) if isinstance(obj, tuple) else new
     return obj
 
 
@@ -114,7 +118,7 @@ def all_reduce_gradients(params: List[torch.Tensor]) -> None:
     if not params:
         return
     dev = params[0].device
-    if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+    if UNIFORM_GRADS or (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):
         # inside a CUDA-graph capture no host read-back is possible: gradients that are None must be None on
         # every rank (true for this path: the same graph runs everywhere), so only the present ones travel
         live = [p for p in params if p.grad is not None]
@@ -145,6 +149,7 @@ def all_reduce_gradients(params: List[torch.Tensor]) -> None:
 
 
 _HOOK_INSTALLED = False
+UNIFORM_GRADS = False   # True: a gradient that is None on one rank is None on all (skips the presence flags + host sync)
 
 
 def _install_optimizer_hook() -> None:
@@ -217,7 +222,7 @@ class training_wrapper_class(torch.nn.Module):
             render_kwargs_train["network_fine"] = self.fine_model
         dev = target_s.device
         latent_table = torch.stack(self.latents, dim=0).to(dev)                      # [T, Z]
-        key = id(dataset_extras["imageid_to_timestepid"])
+        key = tuple(dataset_extras["imageid_to_timestepid"])
         if getattr(self, "_i2t", (None, None))[0] != (key, dev):   # one H2D copy, not one per step (train.py:178-180)
             self._i2t = ((key, dev), torch.as_tensor(dataset_extras["imageid_to_timestepid"], device=dev))
         imageid_to_timestepid = self._i2t[1]
