@@ -179,6 +179,29 @@ typedef struct NrnDivArgs {
 int nrn_divergence_forward(const NrnDivArgs* args);
 int nrn_divergence_backward(const NrnDivArgs* args);
 
+/* ---- per-ray training loss of training_wrapper_class.forward (train.py:208-242): image terms (fine +
+ * coarse) and the offsets / rigidity regulariser on the coarse samples, with the gradients per unit
+ * upstream gradient written in the same pass (the loss is linear in dL/dloss[ray]). ----------------- */
+typedef struct NrnRayLossArgs {
+  int32_t n_rays, n_samples;
+  const float* rgb;                /* [n][3] rgb_map */
+  const float* rgb0;               /* [n][3] coarse rgb_map or NULL */
+  const float* target;             /* [n][3] */
+  const float* weights;            /* [n][S] coarse visibility weights (detached) or NULL */
+  const float* unmasked_offsets;   /* [n][S][3] or NULL: no offsets term */
+  const float* rigidity_mask;      /* [n][S] */
+  float lam_offsets;               /* offsets_loss_weight * (1/100)^(1 - global_step / N_iters) */
+  float lam_rigidity;              /* rigidity_loss_weight */
+  float* loss;                     /* out [n] */
+  float* u_rgb; float* u_rgb0;     /* out [n][3]: d loss / d rgb, d loss / d rgb0 */
+  float* u_unmasked_offsets;       /* out [n][S][3] */
+  float* u_rigidity_mask;          /* out [n][S] */
+  void* stream;
+} NrnRayLossArgs;
+int nrn_ray_loss(const NrnRayLossArgs* args);
+/* out[i] = g[i / per_row] * unit[i]  (backward of nrn_ray_loss) */
+int nrn_scale_rows(const float* g, const float* unit, float* out, int64_t n, int per_row, void* stream);
+
 /* ---- optional per-kernel timing (measurement aid for bench.py) ---------------------------------
  * While enabled, every launch of the kernel kinds below is bracketed by CUDA events recorded on the
  * launch stream.  kinds: 0 field forward, 1 field DGRAD, 2 WGRAD (+reduce), 3 composite(+resample),

@@ -59,6 +59,16 @@ class NrnDivArgs(C.Structure):
     ]
 
 
+class NrnRayLossArgs(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int32), ("n_samples", C.c_int32),
+        ("rgb", _vp), ("rgb0", _vp), ("target", _vp), ("weights", _vp), ("unmasked_offsets", _vp), ("rigidity_mask", _vp),
+        ("lam_offsets", C.c_float), ("lam_rigidity", C.c_float),
+        ("loss", _vp), ("u_rgb", _vp), ("u_rgb0", _vp), ("u_unmasked_offsets", _vp), ("u_rigidity_mask", _vp),
+        ("stream", _vp),
+    ]
+
+
 class NrnCompositeArgs(C.Structure):
     _fields_ = [
         ("raw", _vp), ("z_vals", _vp), ("rays_d", _vp), ("rays_d_stride", C.c_int32), ("noise", _vp),
@@ -102,6 +112,8 @@ SYMBOLS = {
     "nrn_div_grad_stash_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "nrn_divergence_forward": (C.c_int, [C.POINTER(NrnDivArgs)]),
     "nrn_divergence_backward": (C.c_int, [C.POINTER(NrnDivArgs)]),
+    "nrn_ray_loss": (C.c_int, [C.POINTER(NrnRayLossArgs)]),
+    "nrn_scale_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
     "nrn_timing_enable": (C.c_int, [C.c_int]),
     "nrn_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }

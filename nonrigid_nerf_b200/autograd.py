@@ -264,6 +264,66 @@ def _flat_params_bender(bender):
     return None, bend
 
 
+class _RayLossFn(torch.autograd.Function):
+    """Per-ray loss of training_wrapper_class.forward (train.py:208-242) in one kernel (csrc/loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, rgb, rgb0, target, weights, unmasked, rigidity, lam_o, lam_r):
+        n = rgb.shape[0]
+        dev = rgb.device
+        lib = _lib.load()
+        a = _lib.NrnRayLossArgs()
+        keep = [rgb.detach().contiguous().float(), target.contiguous().float()]
+        a.rgb, a.target = keep[0].data_ptr(), keep[1].data_ptr()
+        u_rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        a.u_rgb = u_rgb.data_ptr()
+        u_rgb0 = u_off = u_rig = None
+        if rgb0 is not None:
+            keep.append(rgb0.detach().contiguous().float())
+            a.rgb0 = keep[-1].data_ptr()
+            u_rgb0 = torch.empty(n, 3, dtype=torch.float32, device=dev)
+            a.u_rgb0 = u_rgb0.data_ptr()
+        s = 1
+        if unmasked is not None:
+            s = unmasked.shape[1]
+            keep += [weights.detach().contiguous().float(), unmasked.detach().contiguous().float(), rigidity.detach().contiguous().float()]
+            a.weights, a.unmasked_offsets, a.rigidity_mask = (t.data_ptr() for t in keep[-3:])
+            u_off = torch.empty(n, s, 3, dtype=torch.float32, device=dev)
+            u_rig = torch.empty(rigidity.shape, dtype=torch.float32, device=dev)
+            a.u_unmasked_offsets, a.u_rigidity_mask = u_off.data_ptr(), u_rig.data_ptr()
+        a.n_rays, a.n_samples = n, s
+        a.lam_offsets, a.lam_rigidity = float(lam_o), float(lam_r)
+        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        a.loss = loss.data_ptr()
+        a.stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(dev):
+            _lib.check(lib.nrn_ray_loss(C.byref(a)), "ray_loss")
+        ctx.units = (u_rgb, u_rgb0, u_off, u_rig)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        g = g.contiguous().float()
+        outs = []
+        for u in ctx.units:
+            if u is None:
+                outs.append(None)
+                continue
+            o = torch.empty_like(u)
+            with torch.cuda.device(u.device):
+                _lib.check(lib.nrn_scale_rows(C.c_void_p(g.data_ptr()), C.c_void_p(u.data_ptr()), C.c_void_p(o.data_ptr()), u.numel(),
+                                              u.numel() // g.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "scale_rows")
+            outs.append(o)
+        d_rgb, d_rgb0, d_off, d_rig = outs
+        return d_rgb, d_rgb0, None, None, d_off, d_rig, None, None
+
+
+def ray_loss(rgb, rgb0, target, weights=None, unmasked=None, rigidity=None, lam_offsets=0.0, lam_rigidity=0.0):
+    """loss[N] = img2mse(rgb) + img2mse(rgb0) + lam_offsets * (offsets + lam_rigidity * rigidity regulariser)."""
+    return _RayLossFn.apply(rgb, rgb0, target, weights, unmasked, rigidity, lam_offsets, lam_rigidity)
+
+
 class _CompositeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd, n_importance, u):

@@ -10,6 +10,7 @@
 #include "ray_ops.cuh"
 #include "wgrad.cuh"
 #include "div.cuh"
+#include "loss.cuh"
 
 namespace nrn {
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
@@ -360,6 +361,30 @@ int nrn_divergence_backward(const NrnDivArgs* a) {
   w.n_tiles = static_cast<int>((p.P + nrn::kTileM - 1) / nrn::kTileM); w.err = ds->err_word;
   { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, true, ds->num_sms, nullptr, 0, a->bender_grad, nrn_bender_grad_floats(), 5, st); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "wgrad_kernel (divergence)");
+}
+
+int nrn_ray_loss(const NrnRayLossArgs* a) {
+  if (!a) return fail(NRN_E_INVALID, "nrn_ray_loss: null args");
+  if (a->n_rays < 0 || a->n_samples < 1) return fail(NRN_E_INVALID, "nrn_ray_loss: bad sizes");
+  if (a->n_rays == 0) return NRN_OK;
+  if (!a->rgb || !a->target || !a->loss || !a->u_rgb || (a->rgb0 && !a->u_rgb0)) return fail(NRN_E_INVALID, "nrn_ray_loss: null argument");
+  if (a->unmasked_offsets && (!a->weights || !a->rigidity_mask || !a->u_unmasked_offsets || !a->u_rigidity_mask))
+    return fail(NRN_E_INVALID, "nrn_ray_loss: the offsets term needs weights, rigidity_mask and both gradient outputs");
+  nrn::RayLossParams p{};
+  p.n = a->n_rays; p.S = a->n_samples;
+  p.rgb = a->rgb; p.rgb0 = a->rgb0; p.target = a->target; p.w = a->weights; p.off = a->unmasked_offsets; p.rig = a->rigidity_mask;
+  p.lam_o = a->lam_offsets; p.lam_r = a->lam_rigidity;
+  p.loss = a->loss; p.u_rgb = a->u_rgb; p.u_rgb0 = a->u_rgb0; p.u_off = a->u_unmasked_offsets; p.u_rig = a->u_rigidity_mask;
+  cudaError_t e = nrn::launch_ray_loss(p, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_loss_kernel");
+}
+
+int nrn_scale_rows(const float* g, const float* unit, float* out, int64_t n, int per_row, void* stream) {
+  if (n < 0 || per_row < 1) return fail(NRN_E_INVALID, "nrn_scale_rows: bad sizes");
+  if (n == 0) return NRN_OK;
+  if (!g || !unit || !out) return fail(NRN_E_INVALID, "nrn_scale_rows: null argument");
+  cudaError_t e = nrn::launch_ray_loss_scale(g, unit, out, n, per_row, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_loss_scale_kernel");
 }
 
 int nrn_timing_enable(int on) {

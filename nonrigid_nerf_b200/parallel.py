@@ -122,13 +122,14 @@ def all_reduce_gradients(params: List[torch.Tensor]) -> None:
         # inside a CUDA-graph capture no host read-back is possible: gradients that are None must be None on
         # every rank (true for this path: the same graph runs everywhere), so only the present ones travel
         live = [p for p in params if p.grad is not None]
-        flat = torch.cat([p.grad.reshape(-1).float() for p in live])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        o = 0
+        flat = torch.cat([p.grad.reshape(-1) for p in live])          # one gather kernel
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)                    # ONE collective over every gradient
+        views, o = [], 0
         for p in live:
             n = p.numel()
-            p.grad.copy_(flat[o:o + n].view_as(p))
+            views.append(flat[o:o + n].view_as(p))
             o += n
+        torch._foreach_copy_([p.grad for p in live], views)            # one multi-tensor scatter back
         return
     chunks = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
     flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], dtype=torch.float32, device=dev)
@@ -232,17 +233,14 @@ class training_wrapper_class(torch.nn.Module):
         detailed = args.offsets_loss_weight > 0.0 or args.divergence_loss_weight > 0.0
         rgb, disp, acc, extras = T.render(rays_o, rays_d, chunk=args.chunk, verbose=i < 10, retraw=True,
                                           additional_pixel_information=info, detailed_output=detailed, **render_kwargs_train)
-        loss = H.img2mse(rgb, target_s, n_rays)
-        if "rgb0" in extras:
-            loss = loss + H.img2mse(extras["rgb0"], target_s, n_rays)
         sched = (1.0 / 100.0) ** (1 - (global_step / args.N_iters))                   # increasing schedule
-        if self.ray_bender is not None and args.offsets_loss_weight > 0.0:
-            w = extras["visibility_weights"].detach().reshape(-1)
-            off_norm = torch.norm(extras["unmasked_offsets"].reshape(-1, 3), dim=-1)
-            rig = extras["rigidity_mask"].reshape(-1)
-            offsets_loss = torch.mean((w * torch.pow(off_norm, 2.0 - rig)).view(n_rays, -1), dim=-1)
-            offsets_loss = offsets_loss + args.rigidity_loss_weight * torch.mean((w * rig).view(n_rays, -1), dim=-1)
-            loss = loss + args.offsets_loss_weight * sched * offsets_loss
+        use_offsets = self.ray_bender is not None and args.offsets_loss_weight > 0.0
+        # data term (fine + coarse) and offsets / rigidity regulariser (train.py:208-242) in one fused kernel
+        loss = _ag.ray_loss(rgb, extras.get("rgb0"), target_s,
+                            extras["visibility_weights"] if use_offsets else None,
+                            extras["unmasked_offsets"] if use_offsets else None,
+                            extras["rigidity_mask"] if use_offsets else None,
+                            args.offsets_loss_weight * sched if use_offsets else 0.0, args.rigidity_loss_weight)
         if self.ray_bender is not None and args.divergence_loss_weight > 0.0:
             # exact_divergence = False, backprop_into_weights = False (train.py:246-247); fused closed-form kernel
             w = 1.0 - torch.exp(-F.relu(extras["opacity_alpha"].detach()))
