@@ -208,7 +208,24 @@ def main():
     pool = 8
     host = [synth_batch(rs, n_global, n_images) for _ in range(pool)]
     pinned = [[torch.from_numpy(a).pin_memory() for a in b] for b in host]
-    resident = [[t.to(dev) for t in b] for b in pinned]
+
+    def to_device_packed(batch):
+        """One flat device buffer per batch; the four tensors are views into it, so that the multi-GPU input
+        broadcast is ONE collective."""
+        sizes = [t.numel() * t.element_size() for t in batch]
+        offs = [0]
+        for sz in sizes:
+            offs.append((offs[-1] + sz + 15) // 16 * 16)
+        flat = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
+        views = []
+        for t, o, sz in zip(batch, offs, sizes):
+            v = flat[o:o + sz].view(t.dtype).view(t.shape)
+            v.copy_(t, non_blocking=True)
+            views.append(v)
+        return flat, views
+
+    packed = [to_device_packed(b) for b in pinned]
+    resident = [v for _, v in packed]
 
     def eager_step(rays_o, rays_d, target, idx):
         losses = train_fn(targs, rays_o, rays_d, 100, render_kwargs_train, target, 1000, 0, dataset_extras, idx)
@@ -244,13 +261,14 @@ def main():
             graphed = None
             torch.cuda.synchronize()
 
-    def step(i, batch):
+    def step(i, batch, batch_flat=None):
         if graphed is None:
             return eager_step(*batch)
         if world == 1:
             return graphed(*batch)
-        for t in batch:                       # every rank uses rank 0's batch (the reference samples with unseeded numpy)
-            dist.broadcast(t, src=0)
+        if batch_flat is None:
+            batch_flat = packed[i % pool][0]
+        dist.broadcast(batch_flat, src=0)     # every rank uses rank 0's batch (the reference samples with unseeded numpy)
         losses_local = graphed(*[t[lo:hi] for t in batch])
         optimizer.step()                      # pre-step hook: one flat gradient all-reduce, then Adam on every rank
         gathered = torch.empty(world * (hi - lo), dtype=losses_local.dtype, device=dev)
@@ -268,8 +286,8 @@ def main():
         e0.record()
         for i in range(loop_steps):
             if e2e:
-                b = [t.to(dev, non_blocking=True) for t in pinned[i % pool]]
-                loss = step(i, b)
+                flat, b = to_device_packed(pinned[i % pool])   # host -> device copy of this step's inputs (pinned memory)
+                loss = step(i, b, flat)
                 loss.item()                      # device -> host read of the step's result
             else:
                 step(i, resident[i % pool])
@@ -319,20 +337,26 @@ def main():
     dom_ms_per_step = per_step[dom]
     flops_per_step = args.n_rand * POINTS_PER_RAY * FLOP_PER_POINT
     achieved = flops_per_step / (dom_ms_per_step * 1e-3) / 1e12
+    # DRAM bytes of that kernel kind (coarse + fine launch), from the committed `ncu --set full` capture of this workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.n_rand == N_RAND:
+        with open(tpath) as f:
+            traffic = json.load(f).get(dom)
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16 tensor-core operands, f32 accumulate", "data": "synthetic",
+        "dtype": "f16 (tensor-core operands; f32 accumulate)", "data": "synthetic",
         "config": {"workload": f"example_sequence training step: N_rand={args.n_rand}/GPU, 64c+128f, 8x256 MLP, ray bending on, "
                                "perturb=1, raw_noise_std=1, offsets+rigidity+divergence regularisers, backward, Adam",
                    "parallelism": f"ray-sharded x{world}, one flat NCCL grad all-reduce per step",
                    "l2": "per-step working set (activation + gradient stash ~1.9 GB) exceeds the 126 MB L2; 8 rotating input batches"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(sum(a.nbytes for a in host[0])),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": 28 * args.steps,
+        "gpu_launches": 25 * args.steps,
         "kernel_ms_per_step": per_step, "cuda_graph": graphed is not None,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
                      "note": "algorithmic FLOPs per step of this kernel kind (coarse + fine launch) = N_rand x 192 x 1,016,320"},
         "clocks": clocks,
     }

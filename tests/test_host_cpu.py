@@ -115,11 +115,12 @@ class _ToyStep(torch.nn.Module):
         return ((pred - target) ** 2).mean(-1) * scale
 
 
-def _worker(rank, world, port, n, out_path):
+def _worker(rank, world, port, n, out_path, uniform):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
     from nonrigid_nerf_b200 import parallel as P
+    P.UNIFORM_GRADS = uniform
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
     dead = torch.nn.Parameter(torch.zeros(3))            # never used: its grad must stay None on every rank
@@ -141,10 +142,11 @@ def _worker(rank, world, port, n, out_path):
     dist.destroy_process_group()
 
 
-def test_ray_sharded_function_matches_single_process(tmp_path):
+@pytest.mark.parametrize("uniform", [False, True])
+def test_ray_sharded_function_matches_single_process(tmp_path, uniform):
     n, world = 11, 2          # uneven shards: 6 + 5 rows
     out = str(tmp_path / "r0.pt")
-    mp.spawn(_worker, args=(world, _free_port(), n, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, out, uniform), nprocs=world, join=True)
     got = torch.load(out)
     # single-process run on rank 0's batches
     torch.manual_seed(0)
