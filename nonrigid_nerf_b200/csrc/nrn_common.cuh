@@ -143,7 +143,7 @@ struct FieldFwdParams {
   float* d_masked;        // [P][3] or null
   float* d_rigid;         // [P]    or null
   uint8_t* stash;         // training stash [n_tiles rounded up to even][kStashTileBytes] or null
-  int debug_mode;         // developer experiments (NRN_DEBUG_MODE): 1 = epilogues skip their work, 2 = no MMAs issued
+  int debug_mode;         // developer experiments (NRN_DEBUG_MODE): 1 = epilogues skip their work, 2 = no MMAs issued, 3 = 1 + no weight streaming
   int* err;               // device error word (0 = ok)
 };
 

@@ -191,6 +191,70 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2, tcgen05 cta_group::2): one MMA spans both CTAs' tensor memory (M = 256),
+// each CTA supplies its own 128 rows of A and half of B.  Validated by tests/cuda/umma2_probe.cu.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// Arrive on the barrier at the same shared-memory offset in CTA `target_cta`.  Default semantics (release at CTA
+// scope): the data it publishes is shared memory of THIS CTA, already fenced for the async proxy, and read by this
+// SM's own tensor core.  A .release.cluster arrive measured ~0.7 us (it drains the thread's global stores).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* local_bar, uint32_t target_cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_bar)), "r"(target_cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(raddr) : "memory");
+}
+// try_wait with acquire at cluster scope: pairs with mbar_arrive_cluster from the peer CTA
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Whole-warp calls, executed by the same warp of BOTH CTAs of the pair.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// Issued by one thread of the LEADER CTA (rank 0); descriptors hold leader-local shared addresses, the
+// hardware applies the same offsets in the peer CTA.
+__device__ __forceinline__ void umma_f16_ss2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed.
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM -> registers. Warp w of a CTA may only touch lanes [32*(w%4), 32*(w%4)+32).
 // 32x32b.xN: thread i of the warp receives lane (base_lane+i), N consecutive 32-bit columns.
 // ----------------------------------------------------------------------------------------------

@@ -24,19 +24,11 @@ using namespace nrn;
   } while (0)
 
 struct Cfg {
-  int N, K;
+  int N, K, remote_bar;   // remote_bar: the peer's bulk copies complete_tx on the LEADER's mbarrier (no relay needed)
   uint32_t a_bytes, b_bytes;  // per CTA
   uint32_t idesc;
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void remote_arrive(uint64_t* local_bar, uint32_t target_cta) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(local_bar)), "r"(target_cta));
@@ -71,20 +63,29 @@ probe2_kernel(Cfg cfg, const uint8_t* __restrict__ a_img, const uint8_t* __restr
   const uint32_t tmem_base = tmem_base_s;
 
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(&bar_load, cfg.a_bytes + cfg.b_bytes);
+    uint32_t bar_addr = smem_u32(&bar_load);
+    if (cfg.remote_bar) {
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar_addr) : "r"(smem_u32(&bar_load)), "r"(0u));
+      if (rank == 0) mbar_arrive_expect_tx(&bar_load, 2u * (cfg.a_bytes + cfg.b_bytes));
+    } else {
+      mbar_arrive_expect_tx(&bar_load, cfg.a_bytes + cfg.b_bytes);
+    }
     const uint8_t* ga = a_img + static_cast<size_t>(rank) * cfg.a_bytes;
     const uint8_t* gb = b_img + static_cast<size_t>(rank) * cfg.b_bytes;
-    for (uint32_t off = 0; off < cfg.a_bytes; off += 16384u)
-      tma_bulk_g2s(sa + off, ga + off, cfg.a_bytes - off < 16384u ? cfg.a_bytes - off : 16384u, &bar_load);
-    for (uint32_t off = 0; off < cfg.b_bytes; off += 16384u)
-      tma_bulk_g2s(sb + off, gb + off, cfg.b_bytes - off < 16384u ? cfg.b_bytes - off : 16384u, &bar_load);
+    auto copy = [&](uint8_t* dst, const uint8_t* src, uint32_t n) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                   "l"(src), "r"(n), "r"(bar_addr)
+                   : "memory");
+    };
+    for (uint32_t off = 0; off < cfg.a_bytes; off += 16384u) copy(sa + off, ga + off, cfg.a_bytes - off < 16384u ? cfg.a_bytes - off : 16384u);
+    for (uint32_t off = 0; off < cfg.b_bytes; off += 16384u) copy(sb + off, gb + off, cfg.b_bytes - off < 16384u ? cfg.b_bytes - off : 16384u);
   }
   if (warp == 1 && lane == 0) {
-    bool ok = mbar_wait(&bar_load, 0, err, 11);
+    bool ok = (cfg.remote_bar && rank == 1) ? true : mbar_wait(&bar_load, 0, err, 11);
     if (rank == 1) {
-      if (ok) remote_arrive(&bar_peer, 0);   // tell the leader that this CTA's operands have landed
+      if (ok && !cfg.remote_bar) remote_arrive(&bar_peer, 0);   // tell the leader that this CTA's operands have landed
     } else {
-      ok = ok && mbar_wait(&bar_peer, 0, err, 12);
+      ok = ok && (cfg.remote_bar || mbar_wait(&bar_peer, 0, err, 12));
       tc_fence_after_sync();
       if (ok) {
         const uint32_t half_rows = cfg.N / 2;
@@ -134,7 +135,7 @@ static void image(const std::vector<uint16_t>& m, int r0, int R, int C, std::vec
     for (int c = 0; c < C; ++c) out[base + (size_t)(c / 8) * R * 8 + (size_t)r * 8 + (c % 8)] = m[(size_t)(r0 + r) * C + c];
 }
 
-static int run_case(int N, int K) {
+static int run_case(int N, int K, int remote_bar) {
   const int M = 256;
   std::vector<uint16_t> A((size_t)M * K), B((size_t)N * K);
   for (auto& v : A) v = f2h(frand());
@@ -143,7 +144,7 @@ static int run_case(int N, int K) {
   image(A, 0, 128, K, a_img); image(A, 128, 128, K, a_img);
   image(B, 0, N / 2, K, b_img); image(B, N / 2, N / 2, K, b_img);
   Cfg cfg{};
-  cfg.N = N; cfg.K = K;
+  cfg.N = N; cfg.K = K; cfg.remote_bar = remote_bar;
   cfg.a_bytes = 128 * K * 2; cfg.b_bytes = (N / 2) * K * 2;
   cfg.idesc = umma_instr_desc(256, N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
   uint8_t *da, *db; float* dd; int* de;
@@ -169,7 +170,7 @@ static int run_case(int N, int K) {
       if (!(d <= 1e-2 + 1e-3 * fabs(acc))) { ++bad; if (m < 128) ++bad_top; }
       if (d > maxerr || d != d) maxerr = d;
     }
-  printf("[cta_group::2 M=256 N=%3d K=%3d] err=%d bad=%d/%d (rows<128: %d) maxerr=%.3e -> %s\n", N, K, err, bad, M * N, bad_top, maxerr,
+  printf("[cta_group::2 M=256 N=%3d K=%3d remote_bar=%d] err=%d bad=%d/%d (rows<128: %d) maxerr=%.3e -> %s\n", N, K, remote_bar, err, bad, M * N, bad_top, maxerr,
          (bad == 0 && err == 0) ? "PASS" : "FAIL");
   cudaFree(da); cudaFree(db); cudaFree(dd); cudaFree(de);
   return (bad == 0 && err == 0) ? 0 : 1;
@@ -179,11 +180,12 @@ int main() {
   srand(4321);
   int fails = 0;
   const int cases[][2] = {{256, 64}, {256, 256}, {96, 96}, {80, 96}, {64, 64}, {16, 256}, {48, 96}};
-  for (auto& c : cases) {
-    const int r = run_case(c[0], c[1]);
-    if (r == 2) { printf("aborting after kernel error\n"); return 2; }
-    fails += r;
-  }
+  for (int rb = 0; rb < 2; ++rb)
+    for (auto& c : cases) {
+      const int r = run_case(c[0], c[1], rb);
+      if (r == 2) { printf("aborting after kernel error\n"); return 2; }
+      fails += r;
+    }
   printf("2-CTA probe done: %d failing cases\n", fails);
   return fails ? 1 : 0;
 }
