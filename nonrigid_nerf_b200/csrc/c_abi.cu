@@ -13,8 +13,9 @@
 #include "loss.cuh"
 
 namespace nrn {
-cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, bool pair, int num_sms, cudaStream_t stream);
-cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, bool pair, int num_sms, cudaStream_t stream);
+cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
+cudaError_t launch_field_fwd2(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
+cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 }
 
 namespace {
@@ -53,7 +54,9 @@ int device_state(DeviceState** out) {
     if (prop.major != 10) return fail(NRN_E_INVALID, "nrnerf_b200 needs an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
     s.num_sms = prop.multiProcessorCount;
     if (const char* g = getenv("NRN_GRID")) { const int v = atoi(g); if (v > 0 && v < s.num_sms) s.num_sms = v; }   // developer experiments
-    s.pair = false;  // NRN_PAIR=1: CTA-pair kernels (tcgen05 cta_group::2), under development
+    // forward field kernel: single-CTA kernel (field_fwd.cu) by default; NRN_PAIR=1 selects the CTA-pair kernel
+    // (field_fwd2.cu, tcgen05 cta_group::2), which measures within +-5% of it
+    s.pair = false;
     if (const char* g = getenv("NRN_PAIR")) s.pair = atoi(g) != 0;
     e = cudaMalloc(&s.err_word, 4 * sizeof(int));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(err word)");
@@ -203,7 +206,8 @@ int nrn_field_forward(const NrnFieldArgs* a) {
   { const char* dm = getenv("NRN_DEBUG_MODE"); p.debug_mode = dm ? atoi(dm) : 0; }
   if (a->stash && a->points) return fail(NRN_E_INVALID, "nrn_field_forward: the training stash needs ray mode");
   p.err = ds->err_word;
-  cudaError_t e; { ScopedTimer tm(0, static_cast<cudaStream_t>(a->stream)); e = nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->pair, ds->num_sms, static_cast<cudaStream_t>(a->stream)); }
+  cudaError_t e; { ScopedTimer tm(0, static_cast<cudaStream_t>(a->stream)); e = ds->pair ? nrn::launch_field_fwd2(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream))
+                 : nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream)); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "field_fwd_kernel");
 }
 
@@ -298,7 +302,7 @@ int nrn_field_backward(const NrnFieldBwdArgs* a) {
   p.d_latents = a->d_latents; p.err = ds->err_word;
   e = nrn::launch_absmax(a->d_raw, p.P * a->out_ch, amax, st);
   if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
-  { ScopedTimer tm(1, st); e = nrn::launch_field_bwd(p, bend, ds->pair, ds->num_sms, st); }
+  { ScopedTimer tm(1, st); e = nrn::launch_field_bwd(p, bend, ds->num_sms, st); }
   if (e != cudaSuccess) return cuda_fail(e, "field_bwd_kernel");
   nrn::WgradParams w{};
   w.stash = p.stash; w.gstash = p.gstash; w.scratch = a->wgrad_scratch; w.amax = amax; w.n_tiles = p.n_tiles; w.err = ds->err_word;

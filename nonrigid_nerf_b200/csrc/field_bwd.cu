@@ -5,9 +5,8 @@
 // layer's pre-activation ("dY_l"), the per-ray latent gradient, and -- through the gradient stash --
 // the inputs of the weight-gradient kernel (wgrad.cu).  SURVEY.md appendix C is the specification.
 //
-// Same machine as field_fwd.cu: persistent CTA (or CTA pair sharing every MMA, cta_group::2), two 128-point
-// slots ping-ponging between a tcgen05.mma issuer and two epilogue warpgroups, weights (here W^T images)
-// streamed by bulk TMA.
+// Same machine as field_fwd.cu: persistent CTA, two 128-point slots ping-ponging between a
+// tcgen05.mma issuer and two epilogue warpgroups, weights (here W^T images) streamed by bulk TMA.
 //   step  0      head^T   dh8 = d_raw . Wout          -> dY7 = dh8 * [h8 > 0]
 //   steps 1,2    L7^T,L6^T                            -> dY6, dY5
 //   step  3      L5e^T    dE  = dY5 . W5[:, :63]      -> PE backward -> d(bent xyz)
@@ -26,18 +25,10 @@ namespace {
 
 constexpr long long kWaitLimitCycles = 1ll << 28;
 constexpr int kBwdRingStages = 3;
-constexpr int kMaxStages = 6;
-template <bool PAIR>
-struct Geo {
-  static constexpr int C = PAIR ? 2 : 1;                          // CTAs per MMA
-  static constexpr int kStages = PAIR ? 6 : kBwdRingStages;       // ring stages
-  static constexpr int kStageBytes = kRingStageBytes / C;         // each CTA holds N/C rows of a slab
-};
 
 struct Shared {
-  uint64_t w_full[kMaxStages];
-  uint64_t w_empty[kMaxStages];
-  uint64_t w_peer[kMaxStages];   // leader only: the peer CTA's half of the slab has landed
+  uint64_t w_full[kBwdRingStages];
+  uint64_t w_empty[kBwdRingStages];
   uint64_t a_ready[2];
   uint64_t d_full[2];
   uint32_t tmem_base;
@@ -78,27 +69,13 @@ struct Waiter {
     }
     return true;
   }
-  // same, acquiring at cluster scope (barriers the peer CTA arrives on)
-  __device__ __forceinline__ bool wait_cluster(uint64_t* bar, uint32_t parity, int code) const {
-    if (mbar_try_wait_cluster(bar, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
-      if (*reinterpret_cast<volatile int*>(s_abort)) return false;
-      if (clock64() - t0 > kWaitLimitCycles) {
-        atomicExch(s_abort, code);
-        atomicCAS(g_err, 0, code);
-        return false;
-      }
-    }
-    return true;
-  }
 };
 
 __device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 
 // dY = dh * [h > 0]: drain NCOLS accumulator columns, mask with the forward activation stashed as
 // fp16 (row pointer `mask_row` into the stash tile), write fp16 to the next A operand (smem); the whole
-// image then goes to the gradient stash with a bulk TMA store (publish() in the kernel body).
+// image then goes to the gradient stash with a bulk TMA store (stash_store in the kernel body).
 template <int NCOLS>
 __device__ __forceinline__ void epi_mask_store(uint32_t taddr, const uint8_t* __restrict__ mask_row,
                                                uint8_t* dst_row) {
@@ -186,40 +163,33 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
 
 }  // namespace
 
-template <bool HAS_BENDER, bool PAIR>
+template <bool HAS_BENDER>
 __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBwdParams p) {
-  using G = Geo<PAIR>;
-  constexpr int C = G::C, kStages = G::kStages, kStageBytes = G::kStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                       // 2 slots x 64 KB gradient operand
-  uint8_t* ring = smem + 2 * kHBytes;        // kStages x kStageBytes
-  Shared* sh = reinterpret_cast<Shared*>(ring + kStages * kStageBytes);
+  uint8_t* ring = smem + 2 * kHBytes;        // kBwdRingStages x 32 KB
+  Shared* sh = reinterpret_cast<Shared*>(ring + kBwdRingStages * kRingStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
-  // work unit: a group of 2*C tiles; tile of (slot, rank) = (group * 2 + slot) * C + rank  (as in field_fwd.cu)
-  const int n_groups = (p.n_tiles + 2 * C - 1) / (2 * C);
-  const int group0 = blockIdx.x / C, group_stride = gridDim.x / C;
+  const int n_pairs = (p.n_tiles + 1) >> 1;
   constexpr int kNumSteps = HAS_BENDER ? 15 : 10;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kBwdRingStages; ++i) {
       mbar_init(&sh->w_full[i], 1);
       mbar_init(&sh->w_empty[i], 1);
-      mbar_init(&sh->w_peer[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sh->a_ready[s], C);    // one elected arrive per epilogue warpgroup of each CTA
+      mbar_init(&sh->a_ready[s], 128);
       mbar_init(&sh->d_full[s], 1);
     }
     sh->abort_flag = 0;
     fence_mbar_init();
   }
-  if (PAIR) cluster_sync_all();         // the peer's barriers exist before anything arrives on them
   if (warp == 2) {
-    if (PAIR) { tmem_alloc2(&sh->tmem_base, 512); tmem_relinquish2(); }
-    else { tmem_alloc(&sh->tmem_base, 512); tmem_relinquish(); }
+    tmem_alloc(&sh->tmem_base, 512);
+    tmem_relinquish();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -231,7 +201,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
     // ===================== weight producer (W^T images) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int group = group0; group < n_groups; group += group_stride) {
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         uint32_t gn = 0, gb = 0;
 #pragma unroll 1
         for (int step = 0; step < kNumSteps; ++step) {
@@ -240,75 +210,49 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
           for (int slot = 0; slot < 2; ++slot) {
             for (uint32_t j = 0; j < s.nslabs; ++j) {
               W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
-              uint8_t* dst = ring + stage * kStageBytes;
-              mbar_arrive_expect_tx(&sh->w_full[stage], s.slab_bytes / C);
+              uint8_t* dst = ring + stage * kRingStageBytes;
+              mbar_arrive_expect_tx(&sh->w_full[stage], s.slab_bytes);
               const uint8_t* g = src + j * s.slab_bytes;
-              if (PAIR) {
-                // this CTA's N/2 rows of every 8-column chunk: [chunk][N rows][16 B] -> [chunk][N/2 rows][16 B]
-                const uint32_t hb = s.N * 8u, nch = s.slab_bytes / (s.N * 16u);
-                for (uint32_t c = 0; c < nch; ++c)
-                  tma_bulk_g2s(dst + c * hb, g + c * 2u * hb + rank * hb, hb, &sh->w_full[stage]);
-              } else {
-                for (uint32_t off = 0; off < s.slab_bytes; off += 16384u) {
-                  const uint32_t n = s.slab_bytes - off < 16384u ? s.slab_bytes - off : 16384u;
-                  tma_bulk_g2s(dst + off, g + off, n, &sh->w_full[stage]);
-                }
+              for (uint32_t off = 0; off < s.slab_bytes; off += 16384u) {
+                const uint32_t n = s.slab_bytes - off < 16384u ? s.slab_bytes - off : 16384u;
+                tma_bulk_g2s(dst + off, g + off, n, &sh->w_full[stage]);
               }
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              if (++stage == kBwdRingStages) { stage = 0; phase ^= 1u; }
             }
           }
           if (step < 10) gn += s.nslabs * s.slab_bytes; else gb += s.nslabs * s.slab_bytes;
         }
       }
     }
-  } else if (warp == 3) {
-    // ===================== peer relay: "my half of the slab has landed" -> leader =====================
-    if (PAIR && rank == 1 && lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int group = group0; group < n_groups; group += group_stride) {
-#pragma unroll 1
-        for (int step = 0; step < kNumSteps; ++step) {
-          const uint32_t n = 2u * step_shape(step).nslabs;
-          for (uint32_t i = 0; i < n; ++i) {
-            W.wait(&sh->w_full[stage], phase, 401);
-            mbar_arrive_cluster(&sh->w_peer[stage], 0);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t aph[2] = {0u, 0u};
-      for (int group = group0; group < n_groups; group += group_stride) {
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
 #pragma unroll 1
         for (int step = 0; step < kNumSteps; ++step) {
           const StepShape s = step_shape(step);
-          const uint32_t idesc = umma_instr_desc(kTileM * C, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
-          const uint32_t b_lbo = (s.N / C) * 16;   // rows of B held by one CTA x 16 B
+          const uint32_t idesc = umma_instr_desc(kTileM, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
           for (int slot = 0; slot < 2; ++slot) {
-            if (PAIR) W.wait_cluster(&sh->a_ready[slot], aph[slot], 201); else W.wait(&sh->a_ready[slot], aph[slot], 201);
+            W.wait(&sh->a_ready[slot], aph[slot], 201);
             aph[slot] ^= 1u;
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + slot * 256;
             const uint32_t a_base = smem_u32(act + slot * kHBytes);
             for (uint32_t j = 0; j < s.nslabs; ++j) {
               W.wait(&sh->w_full[stage], phase, 202);
-              if (PAIR) W.wait_cluster(&sh->w_peer[stage], phase, 203);
               tc_fence_after_sync();
               const uint64_t adesc = umma_smem_desc(a_base + j * 8 * kChunkBytes, kChunkBytes, 128);
-              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kStageBytes), b_lbo, 128);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
               for (uint32_t k = 0; k < s.k16; ++k) {
-                const uint64_t ad = umma_desc_advance(adesc, k * 2 * kChunkBytes), bd = umma_desc_advance(bdesc, k * 2 * b_lbo);
-                if (PAIR) umma_f16_ss2(d_tmem, ad, bd, idesc, (j | k) ? 1u : 0u);
-                else umma_f16_ss(d_tmem, ad, bd, idesc, (j | k) ? 1u : 0u);
+                umma_f16_ss(d_tmem, umma_desc_advance(adesc, k * 2 * kChunkBytes),
+                            umma_desc_advance(bdesc, k * 2 * s.N * 16), idesc, (j | k) ? 1u : 0u);
               }
-              if (PAIR) umma_commit2(&sh->w_empty[stage]); else umma_commit(&sh->w_empty[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              umma_commit(&sh->w_empty[stage]);
+              if (++stage == kBwdRingStages) { stage = 0; phase ^= 1u; }
             }
-            if (PAIR) umma_commit2(&sh->d_full[slot]); else umma_commit(&sh->d_full[slot]);
+            umma_commit(&sh->d_full[slot]);
           }
         }
       }
@@ -320,7 +264,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
     uint8_t* a_row = act + slot * kHBytes + row * 16;
     const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) + slot * 256;
     uint32_t dph = 0;
-    const bool wg_leader = (threadIdx.x & 127) == 0;
+    auto signal_ready = [&]() {
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&sh->a_ready[slot]);
+    };
     auto wait_acc = [&](int code) {
       W.wait(&sh->d_full[slot], dph, code);
       dph ^= 1u;
@@ -338,29 +286,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
     }
     const float inv_scale = 1.0f / scale;
 
-    for (int group = group0; group < n_groups; group += group_stride) {
-      const long long tile = (static_cast<long long>(group) * 2 + slot) * C + rank;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const long long tile = static_cast<long long>(pair) * 2 + slot;
       const long long pt = tile * kTileM + row;
       const bool valid = pt < p.P;
       const uint8_t* st = p.stash + tile * kStashTileBytes + row * 16;
       uint8_t* gs = p.gstash + tile * kGradTileBytes;
       uint8_t* a_img = act + slot * kHBytes;
+      const bool wg_leader = (threadIdx.x & 127) == 0;
       // gradient stash: bulk TMA stores of finished images from shared memory (see field_fwd.cu)
       auto stash_begin = [&]() {
         if (wg_leader) tma_bulk_wait_read<0>();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
       };
-      // publish(): operand image complete -> (bytes > 0: store it to the gradient stash) -> tell the MMA issuer
-      auto publish = [&](uint32_t off, uint32_t bytes) {
+      auto stash_store = [&](uint32_t off, uint32_t bytes) {
         fence_proxy_async_smem();
-        tc_fence_before_sync();
         asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
         if (wg_leader) {
-          if (bytes) {
-            for (uint32_t o = 0; o < bytes; o += 16384u) tma_bulk_s2g(gs + off + o, a_img + o, bytes - o < 16384u ? bytes - o : 16384u);
-            tma_bulk_commit();
-          }
-          if (PAIR) mbar_arrive_cluster(&sh->a_ready[slot], 0); else mbar_arrive(&sh->a_ready[slot]);
+          for (uint32_t o = 0; o < bytes; o += 16384u) tma_bulk_s2g(gs + off + o, a_img + o, bytes - o < 16384u ? bytes - o : 16384u);
+          tma_bulk_commit();
         }
       };
 
@@ -377,8 +321,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         stash_begin();
         *reinterpret_cast<uint4*>(a_row) = c0;
         *reinterpret_cast<uint4*>(a_row + kChunkBytes) = zz;
-        publish(kGsRaw, 2 * kChunkBytes);
+        stash_store(kGsRaw, 2 * kChunkBytes);
       }
+      signal_ready();
       float dx[3] = {0.f, 0.f, 0.f};
       // ---- head^T, L7^T, L6^T : dY7, dY6, dY5 ----
 #pragma unroll 1
@@ -386,19 +331,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         wait_acc(300 + s);
         stash_begin();
         epi_mask_store<256>(taddr, st + kStH + (7 - s) * kHBytes, a_row);
-        publish(kGsY + (7 - s) * kHBytes, kHBytes);
+        stash_store(kGsY + (7 - s) * kHBytes, kHBytes);
+        signal_ready();
       }
       // ---- L5e^T: gradient into the skip-connected embedding ----
       wait_acc(303);
       pe_backward(taddr, st + kStE, dx);
-      publish(0, 0);   // A operand (dY5) untouched; accumulator drained
+      signal_ready();   // A operand (dY5) untouched; accumulator drained
       // ---- L5h^T, L4^T .. L1^T : dY4 .. dY0 ----
 #pragma unroll 1
       for (int s = 0; s < 5; ++s) {
         wait_acc(304 + s);
         stash_begin();
         epi_mask_store<256>(taddr, st + kStH + (4 - s) * kHBytes, a_row);
-        publish(kGsY + (4 - s) * kHBytes, kHBytes);
+        stash_store(kGsY + (4 - s) * kHBytes, kHBytes);
+        signal_ready();
       }
       // ---- L0^T: gradient into the embedding; then through the bend ----
       wait_acc(309);
@@ -435,13 +382,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         stash_begin();
         *reinterpret_cast<uint4*>(a_row) = c0;
         *reinterpret_cast<uint4*>(a_row + kChunkBytes) = zz;
-        publish(kGsYb4, 2 * kChunkBytes);
+        stash_store(kGsYb4, 2 * kChunkBytes);
       }
+      signal_ready();
       // ---- B4^T -> dYb3 ----
       wait_acc(310);
       stash_begin();
       epi_mask_store<64>(taddr, st + kStHb4, a_row);
-      publish(kGsYb3, 8 * kChunkBytes);
+      stash_store(kGsYb3, 8 * kChunkBytes);
+      signal_ready();
       // ---- B3^T -> dYb2 = [dh * mask (64) | d rigidity pre-activation | 0 (15)] ----
       wait_acc(311);
       stash_begin();
@@ -452,16 +401,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         *reinterpret_cast<uint4*>(a_row + 8 * kChunkBytes) = c8;
         *reinterpret_cast<uint4*>(a_row + 9 * kChunkBytes) = zz;
       }
-      publish(kGsYb2, 10 * kChunkBytes);
+      stash_store(kGsYb2, 10 * kChunkBytes);
+      signal_ready();
       // ---- B2^T -> dYb1, B1^T -> dYb0 ----
       wait_acc(312);
       stash_begin();
       epi_mask_store<96>(taddr, st + kStHb2, a_row);
-      publish(kGsYb1, 12 * kChunkBytes);
+      stash_store(kGsYb1, 12 * kChunkBytes);
+      signal_ready();
       wait_acc(313);
       stash_begin();
       epi_mask_store<96>(taddr, st + kStHb1, a_row);
-      publish(kGsYb0, 12 * kChunkBytes);
+      stash_store(kGsYb0, 12 * kChunkBytes);
+      signal_ready();
       // ---- B0^T: d(bender input); columns 6..37 are the latent code -> per-ray reduction ----
       wait_acc(314);
       {
@@ -494,40 +446,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
 
   tc_fence_before_sync();
   __syncthreads();
-  if (PAIR) cluster_sync_all();   // no CTA exits (or frees TMEM) while its peer can still reach it
-  if (warp == 2) { if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool HAS_BENDER, bool PAIR>
-static cudaError_t launch_variant(const FieldBwdParams& p, int num_sms, cudaStream_t stream) {
-  using G = Geo<PAIR>;
-  const size_t smem = 2 * kHBytes + G::kStages * G::kStageBytes + sizeof(Shared) + 64;
-  const int n_groups = (p.n_tiles + 2 * G::C - 1) / (2 * G::C);
-  const int max_groups = num_sms / G::C;
-  const int grid = G::C * (n_groups < max_groups ? n_groups : max_groups);
-  auto kern = field_bwd_kernel<HAS_BENDER, PAIR>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kFwdThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = G::C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, p);
-}
-
-cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, bool pair, int num_sms, cudaStream_t stream) {
-  if (p.n_tiles <= 0) return cudaSuccess;
-  if (has_bender) return pair ? launch_variant<true, true>(p, num_sms, stream) : launch_variant<true, false>(p, num_sms, stream);
-  return pair ? launch_variant<false, true>(p, num_sms, stream) : launch_variant<false, false>(p, num_sms, stream);
+cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, int num_sms, cudaStream_t stream) {
+  const size_t smem = 2 * kHBytes + kBwdRingStages * kRingStageBytes + sizeof(Shared) + 64;
+  const int n_pairs = (p.n_tiles + 1) / 2;
+  if (n_pairs <= 0) return cudaSuccess;
+  const int grid = n_pairs < num_sms ? n_pairs : num_sms;
+  cudaError_t e;
+  if (has_bender) {
+    e = cudaFuncSetAttribute(field_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    field_bwd_kernel<true><<<grid, kFwdThreads, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(field_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    field_bwd_kernel<false><<<grid, kFwdThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace nrn

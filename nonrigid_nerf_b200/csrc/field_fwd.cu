@@ -17,59 +17,20 @@
 //            bias/ReLU/(bend + positional encoding), and writes the next A operand in place.
 //   steps  : B0..B4 (ray bender, offset + rigidity MLPs fused block-diagonally), L0..L7, head
 //
-// Shared memory (per CTA): 2 x (H 64 KB + E 16 KB) activations + 64 KB weight ring + barriers.
+// Shared memory (per CTA): 2 x (H 64 KB + E 16 KB) activations + 2 x 32 KB weight ring + barriers.
 // Tensor memory: 512 columns, 256 per slot.
-//
-// CTA pairs (PAIR = true, the default): two CTAs of a cluster share every MMA (tcgen05 cta_group::2, M = 256:
-// slot s of both CTAs forms one 256-point operand) and each CTA streams only HALF of every weight slab (its
-// N/2 rows).  Per 128 x 256 x 16 MMA a CTA then reads 4 KB of A + 4 KB of B from shared memory instead of
-// 4 + 8 KB and the ring takes half the TMA write traffic: shared-memory bandwidth, not the tensor pipe, was
-// the measured limiter of the single-CTA kernel.  The leader CTA (cluster rank 0) issues
-// the MMAs; completion is multicast to both CTAs' barriers; the peer reports "operands landed" with remote
-// mbarrier arrives.
 #include "nrn_common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace nrn {
 
-#ifdef NRN_TRACE
-// developer instrumentation (make EXTRA=-DNRN_TRACE): time stamps of the handshake chain of cluster 0, third work
-// group.  Every traced thread owns a log region and writes with plain stores (no atomics: tracing must not stall).
-__device__ unsigned long long g_trace_buf[2 * 5 * 256];
-__device__ __forceinline__ void trace_ev(bool on, uint32_t role, uint32_t& cnt, uint32_t ev, uint32_t step, uint32_t slot, uint32_t j) {
-  if (!on || cnt >= 256u) return;
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  g_trace_buf[((blockIdx.x & 1) * 5 + role) * 256 + cnt++] = (t << 20) | ((unsigned long long)(blockIdx.x & 1) << 19) | (ev << 12) | (step << 6) | (slot << 4) | j;
-}
-#define TRACE(role, ev, step, slot, j) trace_ev(trace_on, role, trace_cnt, ev, step, slot, j)
-__device__ long long g_prof[8];   // issuer cycle accounting of CTA 0: total, wait a_ready, wait weights, issue, commit
-#define PROF_DECL long long pf_t = clock64(), pf_acc[5] = {0, 0, 0, 0, 0}; const long long pf_start = pf_t;
-#define PROF(i) { const long long t_ = clock64(); pf_acc[i] += t_ - pf_t; pf_t = t_; }
-#define PROF_END if (blockIdx.x == 0) { g_prof[0] = clock64() - pf_start; for (int i_ = 0; i_ < 5; ++i_) g_prof[1 + i_] = pf_acc[i_]; }
-#else
-#define PROF_DECL
-#define PROF(i)
-#define PROF_END
-#define TRACE(role, ev, step, slot, j)
-#endif
-
 namespace {
 
 constexpr long long kWaitLimitCycles = 1ll << 28;  // ~0.14 s: protocol bug => error flag, not a hang
 
-constexpr int kMaxStages = 4;
-template <bool PAIR>
-struct Geo {
-  static constexpr int C = PAIR ? 2 : 1;                        // CTAs per MMA
-  static constexpr int kStages = PAIR ? 4 : kRingStages;        // ring stages
-  static constexpr int kStageBytes = kRingStageBytes / C;       // each CTA holds N/C rows of a slab
-};
-
 struct Shared {
-  uint64_t w_full[kMaxStages];
-  uint64_t w_empty[kMaxStages];
-  uint64_t w_peer[kMaxStages];   // leader only: the peer CTA's half of the slab has landed
+  uint64_t w_full[kRingStages];
+  uint64_t w_empty[kRingStages];
   uint64_t a_ready[2];
   uint64_t d_full[2];
   uint32_t tmem_base;
@@ -78,31 +39,27 @@ struct Shared {
 
 struct StepShape {
   uint32_t N, nslabs, slab_bytes, k16;
-  bool first, last;   // first / last issue step of a layer: wait for the A operand / hand the accumulator over
 };
 
-// issue steps: 0-4 bender B0..B4, 5 L0, 6-9 L1..L4, 10 L5 (embedding part), 11 L5 (hidden part), 12-13 L6 L7, 14 head.
-// The skip layer L5 = [embedding | h] is issued as two steps accumulating into the same tile so that no step needs
-// more than four ring stages (a CTA pair keeps a whole step resident while both slots use it).
-constexpr int kNumIssueSteps = 15;
+// step index: 0-4 bender B0..B4, 5-12 NeRF L0..L7, 13 head
 __device__ __forceinline__ StepShape step_shape(int step) {
   switch (step) {
-    case 0: return {96u, 1u, (uint32_t)kBendB0Bytes, 3u, true, true};
-    case 1: return {96u, 1u, (uint32_t)kBendB1Bytes, 6u, true, true};
-    case 2: return {80u, 1u, (uint32_t)kBendB2Bytes, 6u, true, true};
-    case 3: return {64u, 1u, (uint32_t)kBendB3Bytes, 4u, true, true};
-    case 4: return {16u, 1u, (uint32_t)kBendB4Bytes, 4u, true, true};
-    case 5: return {256u, 1u, 32768u, 4u, true, true};
-    case 10: return {256u, 1u, 32768u, 4u, true, false};
-    case 11: return {256u, 4u, 32768u, 4u, false, true};
-    case 14: return {16u, 1u, (uint32_t)kNerfHeadBytes, 16u, true, true};
-    default: return {256u, 4u, 32768u, 4u, true, true};
+    case 0: return {96u, 1u, (uint32_t)kBendB0Bytes, 3u};
+    case 1: return {96u, 1u, (uint32_t)kBendB1Bytes, 6u};
+    case 2: return {80u, 1u, (uint32_t)kBendB2Bytes, 6u};
+    case 3: return {64u, 1u, (uint32_t)kBendB3Bytes, 4u};
+    case 4: return {16u, 1u, (uint32_t)kBendB4Bytes, 4u};
+    case 5: return {256u, 1u, 32768u, 4u};
+    case 10: return {256u, 5u, 32768u, 4u};
+    case 13: return {16u, 1u, (uint32_t)kNerfHeadBytes, 16u};
+    default: return {256u, 4u, 32768u, 4u};
   }
 }
 // byte offset (inside a slot's activation region: H at 0, E at kHBytes) of the A operand of slab j
 __device__ __forceinline__ uint32_t a_operand_offset(int step, uint32_t j) {
-  if (step == 0 || step == 5 || step == 10) return kHBytes;   // bender input / embedding live in E
-  if (step < 5 || step == 14) return 0;
+  if (step == 0 || step == 5) return kHBytes;                       // bender input / embedding live in E
+  if (step == 10) return j == 0 ? kHBytes : (j - 1) * 8 * kChunkBytes;  // skip: [embedding | h]
+  if (step < 5 || step == 13) return 0;
   return j * 8 * kChunkBytes;
 }
 
@@ -113,20 +70,6 @@ struct Waiter {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-      if (*reinterpret_cast<volatile int*>(s_abort)) return false;
-      if (clock64() - t0 > kWaitLimitCycles) {
-        atomicExch(s_abort, code);
-        atomicCAS(g_err, 0, code);
-        return false;
-      }
-    }
-    return true;
-  }
-  // same, acquiring at cluster scope (barriers the peer CTA arrives on)
-  __device__ __forceinline__ bool wait_cluster(uint64_t* bar, uint32_t parity, int code) const {
-    if (mbar_try_wait_cluster(bar, parity)) return true;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
       if (*reinterpret_cast<volatile int*>(s_abort)) return false;
       if (clock64() - t0 > kWaitLimitCycles) {
         atomicExch(s_abort, code);
@@ -210,40 +153,33 @@ __device__ __forceinline__ void write_pe(const float (&x)[3], uint8_t* dst_row) 
 
 }  // namespace
 
-template <bool HAS_BENDER, bool PAIR>
+template <bool HAS_BENDER>
 __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFwdParams p) {
-  using G = Geo<PAIR>;
-  constexpr int C = G::C, kStages = G::kStages, kStageBytes = G::kStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                                  // 2 slots x (H | E)
-  uint8_t* ring = smem + 2 * kSlotBytes;                // kStages x kStageBytes
-  Shared* sh = reinterpret_cast<Shared*>(ring + kStages * kStageBytes);
+  uint8_t* ring = smem + 2 * kSlotBytes;                // kRingStages x 32 KB
+  Shared* sh = reinterpret_cast<Shared*>(ring + kRingStages * kRingStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
-  // work unit: a group of 2*C tiles; tile of (slot, rank) = (group * 2 + slot) * C + rank
-  const int n_groups = (p.n_tiles + 2 * C - 1) / (2 * C);
-  const int group0 = blockIdx.x / C, group_stride = gridDim.x / C;
+  const int n_pairs = (p.n_tiles + 1) >> 1;
   constexpr int kFirstStep = HAS_BENDER ? 0 : 5;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kRingStages; ++i) {
       mbar_init(&sh->w_full[i], 1);
       mbar_init(&sh->w_empty[i], 1);
-      mbar_init(&sh->w_peer[i], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sh->a_ready[s], C);    // one elected arrive per epilogue warpgroup of each CTA
+      mbar_init(&sh->a_ready[s], 128);
       mbar_init(&sh->d_full[s], 1);
     }
     sh->abort_flag = 0;
     fence_mbar_init();
   }
-  if (PAIR) cluster_sync_all();         // the peer's barriers exist before anything arrives on them
   if (warp == 2) {
-    if (PAIR) { tmem_alloc2(&sh->tmem_base, 512); tmem_relinquish2(); }
-    else { tmem_alloc(&sh->tmem_base, 512); tmem_relinquish(); }
+    tmem_alloc(&sh->tmem_base, 512);
+    tmem_relinquish();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -251,125 +187,65 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
   const uint32_t tmem_base = sh->tmem_base;
   const Waiter W{&sh->abort_flag, p.err};
 
-  // Weight streaming.  Single CTA: every slot streams the layer's slabs for itself (a 32 KB slab ring cannot hold
-  // a layer).  CTA pair: a CTA holds only half of each slab, so the 4-stage ring holds a whole layer; each slab is
-  // loaded ONCE per tile group and consumed by slot 0, then by slot 1, before its stage is recycled.
-  constexpr int kUses = PAIR ? 1 : 2;   // how many times the producer streams a step's slabs per tile group
   if (warp == 0) {
     // ===================== weight producer: global -> smem ring (bulk TMA) =====================
-    if (lane == 0 && p.debug_mode != 3) {
+    if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      [[maybe_unused]] uint32_t trace_cnt = 0;
-      for (int group = group0; group < n_groups; group += group_stride) {
-        [[maybe_unused]] const bool trace_on = blockIdx.x < 2 && group == group0 + 2 * group_stride;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         uint32_t gb = 0, gn = 0;
 #pragma unroll 1
-        for (int step = kFirstStep; step < kNumIssueSteps; ++step) {
+        for (int step = kFirstStep; step < 14; ++step) {
           const StepShape s = step_shape(step);
           const uint8_t* src = step < 5 ? p.bend_w + gb : p.nerf_w + gn;
-          for (int use = 0; use < kUses; ++use) {
+          for (int slot = 0; slot < 2; ++slot) {
             for (uint32_t j = 0; j < s.nslabs; ++j) {
               W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
-              TRACE(1, 6, step, use, j);
-              uint8_t* dst = ring + stage * kStageBytes;
-              mbar_arrive_expect_tx(&sh->w_full[stage], s.slab_bytes / C);
+              uint8_t* dst = ring + stage * kRingStageBytes;
+              mbar_arrive_expect_tx(&sh->w_full[stage], s.slab_bytes);
               const uint8_t* g = src + j * s.slab_bytes;
-              if (PAIR) {
-                // this CTA's N/2 rows of every 8-column chunk: [chunk][N rows][16 B] -> [chunk][N/2 rows][16 B]
-                const uint32_t hb = s.N * 8u, nch = s.slab_bytes / (s.N * 16u);
-                for (uint32_t c = 0; c < nch; ++c)
-                  tma_bulk_g2s(dst + c * hb, g + c * 2u * hb + rank * hb, hb, &sh->w_full[stage]);
-              } else {
-                for (uint32_t off = 0; off < s.slab_bytes; off += 16384u) {
-                  const uint32_t n = s.slab_bytes - off < 16384u ? s.slab_bytes - off : 16384u;
-                  tma_bulk_g2s(dst + off, g + off, n, &sh->w_full[stage]);
-                }
+              for (uint32_t off = 0; off < s.slab_bytes; off += 16384u) {
+                const uint32_t n = s.slab_bytes - off < 16384u ? s.slab_bytes - off : 16384u;
+                tma_bulk_g2s(dst + off, g + off, n, &sh->w_full[stage]);
               }
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
             }
           }
           if (step < 5) gb += s.nslabs * s.slab_bytes; else gn += s.nslabs * s.slab_bytes;
         }
       }
     }
-  } else if (PAIR && rank == 1 && warp == 1) {
-    // ===================== peer relay: "my half of the slab has landed" -> leader =====================
-    if (lane == 0 && p.debug_mode != 3) {
-      uint32_t stage = 0, phase = 0;
-      [[maybe_unused]] uint32_t trace_cnt = 0;
-      for (int group = group0; group < n_groups; group += group_stride) {
-        [[maybe_unused]] const bool trace_on = blockIdx.x < 2 && group == group0 + 2 * group_stride;
-#pragma unroll 1
-        for (int step = kFirstStep; step < kNumIssueSteps; ++step) {
-          const uint32_t n = step_shape(step).nslabs;
-          for (uint32_t i = 0; i < n; ++i) {
-            W.wait(&sh->w_full[stage], phase, 401);
-            TRACE(2, 7, step, 0, i);
-            mbar_arrive_cluster(&sh->w_peer[stage], 0);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-          }
-        }
-      }
-    }
-  } else if (rank == 0 && warp == 1) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // Per issue step: slot 0's tile, then slot 1's.  Single CTA: each slot consumes its own copy of the slabs.
-    // CTA pair: slot 0 waits for the slabs (both halves), slot 1 re-uses the resident stages and releases them.
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t aph[2] = {0u, 0u};
-      [[maybe_unused]] uint32_t trace_cnt = 0;
-      PROF_DECL
-      for (int group = group0; group < n_groups; group += group_stride) {
-        [[maybe_unused]] const bool trace_on = blockIdx.x < 2 && group == group0 + 2 * group_stride;
+      for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
 #pragma unroll 1
-        for (int step = kFirstStep; step < kNumIssueSteps; ++step) {
+        for (int step = kFirstStep; step < 14; ++step) {
           const StepShape s = step_shape(step);
-          const uint32_t idesc = umma_instr_desc(kTileM * C, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
-          const uint32_t b_lbo = (s.N / C) * 16;   // rows of B held by one CTA x 16 B
-          const uint32_t stage0 = stage, phase0 = phase;
+          const uint32_t idesc = umma_instr_desc(kTileM, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
           for (int slot = 0; slot < 2; ++slot) {
-            PROF(0)
-            if (s.first) {
-              W.wait(&sh->a_ready[slot], aph[slot], 201);
-              aph[slot] ^= 1u;
-              TRACE(0, 1, step, slot, 0);
-              tc_fence_after_sync();
-            }
-            PROF(1)
-            if (PAIR) { stage = stage0; phase = phase0; }
+            W.wait(&sh->a_ready[slot], aph[slot], 201);
+            aph[slot] ^= 1u;
+            tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + slot * 256;
             const uint32_t a_base = smem_u32(act + slot * kSlotBytes);
             for (uint32_t j = 0; j < s.nslabs; ++j) {
-              if ((!PAIR || slot == 0) && p.debug_mode != 3) {
-                W.wait(&sh->w_full[stage], phase, 202);
-                if (PAIR) W.wait(&sh->w_peer[stage], phase, 203);
-                TRACE(0, 2, step, slot, j);
-                tc_fence_after_sync();
-              }
-              PROF(2)
+              W.wait(&sh->w_full[stage], phase, 202);
+              tc_fence_after_sync();
               const uint64_t adesc = umma_smem_desc(a_base + a_operand_offset(step, j), kChunkBytes, 128);
-              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kStageBytes), b_lbo, 128);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
               for (uint32_t k = 0; k < s.k16 && p.debug_mode != 2; ++k) {
-                const uint64_t ad = umma_desc_advance(adesc, k * 2 * kChunkBytes), bd = umma_desc_advance(bdesc, k * 2 * b_lbo);
-                const uint32_t acc = (!s.first || (j | k)) ? 1u : 0u;
-                if (PAIR) umma_f16_ss2(d_tmem, ad, bd, idesc, acc); else umma_f16_ss(d_tmem, ad, bd, idesc, acc);
+                umma_f16_ss(d_tmem, umma_desc_advance(adesc, k * 2 * kChunkBytes),
+                            umma_desc_advance(bdesc, k * 2 * s.N * 16), idesc, (j | k) ? 1u : 0u);
               }
-              PROF(3)
-              // the slab is free (in both CTAs) once the MMAs of its last user retire
-              if (p.debug_mode == 3) {}
-              else if (!PAIR) umma_commit(&sh->w_empty[stage]); else if (slot == 1) umma_commit2(&sh->w_empty[stage]);
-              if (++stage == kStages) { stage = 0; phase ^= 1u; }
-              PROF(4)
+              umma_commit(&sh->w_empty[stage]);  // slab free once these MMAs retire
+              if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
             }
-            if (s.last) {
-              if (PAIR) umma_commit2(&sh->d_full[slot]); else umma_commit(&sh->d_full[slot]);   // accumulator complete
-              TRACE(0, 3, step, slot, 0);
-            }
+            umma_commit(&sh->d_full[slot]);      // accumulator complete
           }
         }
       }
-      PROF_END
     }
   } else if (warp >= 4) {
     // ===================== epilogue warpgroups =====================
@@ -381,44 +257,40 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
     uint8_t* e_row = Es + row * 16;
     const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) + slot * 256;
     uint32_t dph = 0;
-    [[maybe_unused]] uint32_t trace_cnt = 0;
-    const bool wg_leader = (threadIdx.x & 127) == 0;
+    auto signal_ready = [&]() {
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&sh->a_ready[slot]);
+    };
     auto wait_acc = [&](int code) {
       W.wait(&sh->d_full[slot], dph, code);
       dph ^= 1u;
       tc_fence_after_sync();
     };
 
-    for (int group = group0; group < n_groups; group += group_stride) {
-      [[maybe_unused]] const bool trace_on = blockIdx.x < 2 && group == group0 + 2 * group_stride && wg_leader;
-      const long long tile = (static_cast<long long>(group) * 2 + slot) * C + rank;
-      const long long pt = tile * kTileM + row;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      const long long pt = (static_cast<long long>(pair) * 2 + slot) * kTileM + row;
       const bool valid = pt < p.P;
       // Training stash: every finished activation image (a contiguous chunk-major block of shared memory) is
       // written to this tile's stash block with bulk TMA stores issued by one thread of the warpgroup; the
       // epilogue threads spend no load/store slots on it.  stash_begin(): the previous store must have finished
       // READING shared memory before any image is overwritten.
-      uint8_t* st = p.stash ? p.stash + tile * kStashTileBytes : nullptr;
+      uint8_t* st = p.stash ? p.stash + (static_cast<long long>(pair) * 2 + slot) * kStashTileBytes : nullptr;
+      const bool wg_leader = (threadIdx.x & 127) == 0;
       auto stash_begin = [&]() {
         if (st) {
           if (wg_leader) tma_bulk_wait_read<0>();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
         }
       };
-      // publish(): this warpgroup's operand image is complete.  All 128 threads make their shared-memory writes
-      // visible to the async proxy and meet at the warpgroup's named barrier; one thread then stores the image to
-      // the stash (bytes > 0) and arrives on the MMA issuer's barrier -- in the leader CTA for a CTA pair.
-      auto publish = [&](uint32_t stash_off, const uint8_t* img, uint32_t bytes) {
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
-        if (wg_leader) {
-          if (st && bytes) {
+      auto stash_store = [&](uint32_t stash_off, const uint8_t* img, uint32_t bytes) {
+        if (st) {
+          fence_proxy_async_smem();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + slot) : "memory");
+          if (wg_leader) {
             for (uint32_t o = 0; o < bytes; o += 16384u) tma_bulk_s2g(st + stash_off + o, img + o, bytes - o < 16384u ? bytes - o : 16384u);
             tma_bulk_commit();
           }
-          if (PAIR) mbar_arrive_cluster(&sh->a_ready[slot], 0); else mbar_arrive(&sh->a_ready[slot]);
-          TRACE(3 + slot, 5, 0, slot, 0);
         }
       };
       float x[3] = {0.f, 0.f, 0.f};
@@ -465,20 +337,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           pk.w = pack_h2(in[c * 8 + 6], in[c * 8 + 7]);
           *reinterpret_cast<uint4*>(e_row + c * kChunkBytes) = pk;
         }
-        publish(kStBin, Es, 6 * kChunkBytes);
+        stash_store(kStBin, Es, 6 * kChunkBytes);
+        signal_ready();
         // ---- B0, B1: 96 hidden units (64 offset | 32 rigidity) ----
         wait_acc(301);
         stash_begin();
         epi_bias_relu_store<96>(taddr, p.bend_bias, h_row);
-        publish(kStHb1, Hs, 12 * kChunkBytes);
+        stash_store(kStHb1, Hs, 12 * kChunkBytes);
+        signal_ready();
         wait_acc(302);
         stash_begin();
         epi_bias_relu_store<96>(taddr, p.bend_bias + 96, h_row);
-        publish(kStHb2, Hs, 12 * kChunkBytes);
+        stash_store(kStHb2, Hs, 12 * kChunkBytes);
+        signal_ready();
         // ---- B2: 64 offset hidden + rigidity output (column 64) ----
         wait_acc(303);
         stash_begin();
         epi_bias_relu_store<64>(taddr, p.bend_bias + 192, h_row);
+        stash_store(kStHb3, Hs, 8 * kChunkBytes);
         {
           uint32_t v[16];
           tmem_ld16(taddr + 64, v);
@@ -487,12 +363,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           rigidity = (tanhf(rr) + 1.0f) * 0.5f;   // run_nerf_helpers.py:559-561
           if (p.use_cutoff && rigidity <= p.cutoff) rigidity = 0.f;  // :563-564
         }
-        publish(kStHb3, Hs, 8 * kChunkBytes);
+        signal_ready();
         // ---- B3 ----
         wait_acc(304);
         stash_begin();
         epi_bias_relu_store<64>(taddr, p.bend_bias + 272, h_row);
-        publish(kStHb4, Hs, 8 * kChunkBytes);
+        stash_store(kStHb4, Hs, 8 * kChunkBytes);
+        signal_ready();
         // ---- B4: offsets; bend; positional encoding of the bent point -> E ----
         wait_acc(305);
         {
@@ -520,15 +397,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
       }
       stash_begin();
       write_pe(x, e_row);
-      publish(kStE, Es, kEBytes);
+      stash_store(kStE, Es, kEBytes);
+      signal_ready();
       // ---- L0 .. L7 ----
 #pragma unroll 1
       for (int L = 0; L < 8; ++L) {
         wait_acc(310 + L);
-        TRACE(3 + slot, 4, 5 + L, slot, 0);
         stash_begin();
-        if (p.debug_mode != 1 && p.debug_mode != 3) epi_bias_relu_store<256>(taddr, p.nerf_bias + L * 256, h_row);
-        publish(kStH + L * kHBytes, Hs, kHBytes);
+        if (p.debug_mode != 1) epi_bias_relu_store<256>(taddr, p.nerf_bias + L * 256, h_row);
+        stash_store(kStH + L * kHBytes, Hs, kHBytes);
+        signal_ready();
       }
       // ---- head: raw = output_linear(h) (run_nerf_helpers.py:306) ----
       wait_acc(320);
@@ -546,61 +424,35 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           for (int c = 0; c < p.out_ch; ++c) dst[c] = o[c];
         }
       }
-      // the next a_ready arrival is the next group's prologue (which also means TMEM is drained)
+      // the next a_ready arrival is the next pair's prologue (which also means TMEM is drained)
     }
     if (p.stash && (threadIdx.x & 127) == 0) tma_bulk_wait<0>();   // all stash stores complete before the CTA exits
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (PAIR) cluster_sync_all();   // no CTA exits (or frees TMEM) while its peer can still reach it
-  if (warp == 2) { if (PAIR) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool HAS_BENDER, bool PAIR>
-static cudaError_t launch_variant(const FieldFwdParams& p, int num_sms, cudaStream_t stream) {
-  using G = Geo<PAIR>;
-  const size_t smem = 2 * kSlotBytes + G::kStages * G::kStageBytes + sizeof(Shared) + 64;
-  const int n_groups = (p.n_tiles + 2 * G::C - 1) / (2 * G::C);
-  const int max_groups = num_sms / G::C;
-  const int grid = G::C * (n_groups < max_groups ? n_groups : max_groups);
-  auto kern = field_fwd_kernel<HAS_BENDER, PAIR>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kFwdThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = G::C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, p);
-}
+size_t field_fwd_smem_bytes() { return 2 * kSlotBytes + kRingStages * kRingStageBytes + sizeof(Shared) + 64; }
 
-cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, bool pair, int num_sms, cudaStream_t stream) {
-  if (p.n_tiles <= 0) return cudaSuccess;
-  if (has_bender) return pair ? launch_variant<true, true>(p, num_sms, stream) : launch_variant<true, false>(p, num_sms, stream);
-  return pair ? launch_variant<false, true>(p, num_sms, stream) : launch_variant<false, false>(p, num_sms, stream);
+cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream) {
+  const size_t smem = field_fwd_smem_bytes();
+  const int n_pairs = (p.n_tiles + 1) / 2;
+  if (n_pairs <= 0) return cudaSuccess;
+  const int grid = n_pairs < num_sms ? n_pairs : num_sms;
+  cudaError_t e;
+  if (has_bender) {
+    e = cudaFuncSetAttribute(field_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    field_fwd_kernel<true><<<grid, kFwdThreads, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(field_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    field_fwd_kernel<false><<<grid, kFwdThreads, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
 }
-
-#ifdef NRN_TRACE
-extern "C" int dbg_trace_read(unsigned long long* out, int max_n) {
-  if (max_n < 2 * 5 * 256) return -1;
-  cudaMemcpyFromSymbol(out, g_trace_buf, sizeof(unsigned long long) * 2 * 5 * 256);
-  return 2 * 5 * 256;
-}
-extern "C" void dbg_prof_read(long long* out) { cudaMemcpyFromSymbol(out, g_prof, sizeof(long long) * 8); }
-extern "C" void dbg_trace_reset() {
-  void* p = nullptr;
-  cudaGetSymbolAddress(&p, g_trace_buf);
-  cudaMemset(p, 0, sizeof(unsigned long long) * 2 * 5 * 256);
-}
-#endif
 
 }  // namespace nrn

@@ -128,8 +128,15 @@ __device__ __forceinline__ bool locate(const WgradParams& p, int cta, int& job, 
 
 }  // namespace
 
+#ifdef NRN_TRACE
+__device__ long long g_wg_prof[192 * 4];   // per CTA: job, tiles, cycles until the last MMA retired, total cycles
+#endif
+
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+#ifdef NRN_TRACE
+  const long long prof_t0 = clock64();
+#endif
   Shared* sh = reinterpret_cast<Shared*>(smem + kWgStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -256,6 +263,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     // drain: warps 2..5 own TMEM lane quarters (warp % 4)
     W.wait(&sh->done, 0, 302);
     tc_fence_after_sync();
+#ifdef NRN_TRACE
+    if (threadIdx.x == 64) { g_wg_prof[blockIdx.x * 4 + 0] = job_id; g_wg_prof[blockIdx.x * 4 + 1] = t_end - t_begin; g_wg_prof[blockIdx.x * 4 + 2] = clock64() - prof_t0; }
+#endif
     if (have && warp >= 2 && warp < 6) {
       const int q4 = warp & 3;
       const int m = q4 * 32 + lane;
@@ -281,8 +291,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
   }
   tc_fence_before_sync();
   __syncthreads();
+#ifdef NRN_TRACE
+  if (threadIdx.x == 64) g_wg_prof[blockIdx.x * 4 + 3] = clock64() - prof_t0;
+#endif
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
+#ifdef NRN_TRACE
+extern "C" void dbg_wgrad_prof_read(long long* out) { cudaMemcpyFromSymbol(out, g_wg_prof, sizeof(long long) * 192 * 4); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Deterministic reduction of the split partials into the reference's parameter layout.

@@ -134,3 +134,43 @@ def test_sample_coarse_matches_oracle():
     np.testing.assert_allclose(z0.cpu().numpy(), O.stratified_z(near, far, s, None).numpy(), atol=1.3e-7, rtol=0)
     zl = ops.sample_coarse(helpers.rays8(r, dev), s, None, True)
     np.testing.assert_allclose(zl.cpu().numpy(), O.stratified_z(near, far, s, None, lindisp=True).numpy(), rtol=2e-6)
+
+
+def test_cta_pair_forward_kernel_matches_the_single_cta_kernel(tmp_path):
+    """field_fwd2.cu (tcgen05 cta_group::2, NRN_PAIR=1) is a second implementation of the same arithmetic: identical
+    MMA K order and epilogue, so its raw output and point details must equal the default kernel's bit for bit.
+    The choice is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r"""
+import sys, torch
+sys.path.insert(0, %r)
+import oracle.nrnerf_oracle as O
+from tests import helpers
+from nonrigid_nerf_b200 import autograd as ag, ops, _lib
+dev = torch.device("cuda:0")
+coarse, fine, bender, _ = helpers.build_models(O, 11, dev, True)
+out = {}
+for n, s in ((37, 64), (300, 128)):
+    r = O.make_rays(11, n)
+    rays = helpers.rays8(r, dev)
+    z = ops.sample_coarse(rays, s, None, False)
+    for with_b in (True, False):
+        coarse.ray_bender = (bender if with_b else None,)
+        res = ag.field_rays(coarse, rays, z, r["latents"].to(dev) if with_b else None, True)
+        raw = res[0] if isinstance(res, (tuple, list)) else res
+        out[f"raw_{n}_{s}_{int(with_b)}"] = raw.detach().cpu()
+_lib.device_error_check()
+torch.save(out, sys.argv[1])
+""" % root
+    outs = []
+    for pair in ("0", "1"):
+        path = str(tmp_path / f"pair{pair}.pt")
+        env = dict(os.environ, NRN_PAIR=pair)
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=300)
+        outs.append(torch.load(path))
+    assert outs[0].keys() == outs[1].keys() and len(outs[0]) == 4
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
