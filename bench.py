@@ -195,7 +195,8 @@ def main():
     n_images = 86
     latents = [torch.zeros(32, device=dev).normal_(0, 0.1).requires_grad_(True) for _ in range(n_images)]
     grad_vars = latents + list(bender.parameters()) + list(coarse.parameters()) + list(fine.parameters())
-    optimizer = torch.optim.Adam(params=grad_vars, lr=5e-4, betas=(0.9, 0.999), capturable=not args.no_graph, fused=True)  # same Adam as train.py:656-658, PyTorch's fused kernel
+    from nonrigid_nerf_b200 import optim
+    optimizer = optim.Adam(grad_vars, lr=5e-4, betas=(0.9, 0.999))   # train.py:656-658; one launch over a flat parameter buffer
     render_kwargs_train = {"network_query_fn": None, "perturb": 1.0, "N_importance": N_IMPORTANCE, "network_fine": fine,
                            "N_samples": N_SAMPLES, "network_fn": coarse, "ray_bender": bender, "use_viewdirs": False,
                            "white_bkgd": False, "raw_noise_std": 1.0, "ndc": False, "lindisp": False, "near": 0.0022, "far": 1.0024}
@@ -261,7 +262,11 @@ def main():
             graphed = None
             torch.cuda.synchronize()
 
+    lrate, lrate_decay, iteration = 5e-4, 250, [0]
+
     def step(i, batch, batch_flat=None):
+        iteration[0] += 1
+        optimizer.set_lr(lrate * (0.1 ** (iteration[0] / (lrate_decay * 1000))))   # per-iteration decay of train.py:1611-1616
         if graphed is None:
             return eager_step(*batch)
         if world == 1:
@@ -353,7 +358,7 @@ def main():
                    "l2": "per-step working set (activation + gradient stash ~1.9 GB) exceeds the 126 MB L2; 8 rotating input batches"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(sum(a.nbytes for a in host[0])),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": 25 * args.steps,
+        "gpu_launches": 27 * args.steps,   # this repo's kernels per step: 25 render/backward launches + 2 of the optimizer
         "kernel_ms_per_step": per_step, "cuda_graph": graphed is not None,
         "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,

@@ -202,6 +202,28 @@ int nrn_ray_loss(const NrnRayLossArgs* args);
 /* out[i] = g[i / per_row] * unit[i]  (backward of nrn_ray_loss) */
 int nrn_scale_rows(const float* g, const float* unit, float* out, int64_t n, int per_row, void* stream);
 
+/* ---- optimizer step: replaces torch.optim.Adam(params=grad_vars, lr, betas=(0.9, 0.999)) of train.py:656-658 and its
+ * optimizer.step() at train.py:1608.  All trainable tensors live in one flat fp32 buffer (the host side makes the
+ * nn.Parameters views into it); `blocks` (device, int32 x 4 per entry: tensor index, first element inside the tensor,
+ * element count <= 2048, offset inside the flat buffers) maps CUDA blocks to tensors; `grad_ptrs` (device, one
+ * const float* per tensor, NULL = parameter without gradient, skipped like torch does) is where autograd left each
+ * gradient.  lr (scalar) and step (one int64 per tensor, as torch counts steps per parameter) live on the device
+ * (CUDA-graph replay); the call increments the step of every tensor that has a gradient, then applies
+ * m += (g-m)(1-b1); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) m / (sqrt(v)/sqrt(1-b2^t) + eps). */
+typedef struct NrnAdamArgs {
+  void* params;            /* float [total] */
+  void* exp_avg;           /* float [total] */
+  void* exp_avg_sq;        /* float [total] */
+  const void* grad_ptrs;   /* device array of n_tensors pointers */
+  const void* blocks;      /* device array of n_blocks x 4 int32 */
+  int n_tensors, n_blocks;
+  const void* lr;          /* device float */
+  void* step;              /* device int64 [n_tensors] */
+  float beta1, beta2, eps;
+  void* stream;
+} NrnAdamArgs;
+int nrn_adam_step(const NrnAdamArgs* args);
+
 /* ---- optional per-kernel timing (measurement aid for bench.py) ---------------------------------
  * While enabled, every launch of the kernel kinds below is bracketed by CUDA events recorded on the
  * launch stream.  kinds: 0 field forward, 1 field DGRAD, 2 WGRAD (+reduce), 3 composite(+resample),

@@ -69,6 +69,13 @@ class NrnRayLossArgs(C.Structure):
     ]
 
 
+class NrnAdamArgs(C.Structure):
+    _fields_ = [
+        ("params", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("grad_ptrs", _vp), ("blocks", _vp), ("n_tensors", C.c_int32), ("n_blocks", C.c_int32),
+        ("lr", _vp), ("step", _vp), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("stream", _vp),
+    ]
+
+
 class NrnCompositeArgs(C.Structure):
     _fields_ = [
         ("raw", _vp), ("z_vals", _vp), ("rays_d", _vp), ("rays_d_stride", C.c_int32), ("noise", _vp),
@@ -114,6 +121,7 @@ SYMBOLS = {
     "nrn_divergence_backward": (C.c_int, [C.POINTER(NrnDivArgs)]),
     "nrn_ray_loss": (C.c_int, [C.POINTER(NrnRayLossArgs)]),
     "nrn_scale_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
+    "nrn_adam_step": (C.c_int, [C.POINTER(NrnAdamArgs)]),
     "nrn_timing_enable": (C.c_int, [C.c_int]),
     "nrn_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }

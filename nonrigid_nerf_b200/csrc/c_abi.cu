@@ -11,6 +11,7 @@
 #include "wgrad.cuh"
 #include "div.cuh"
 #include "loss.cuh"
+#include "adam.cuh"
 
 namespace nrn {
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
@@ -392,6 +393,22 @@ int nrn_scale_rows(const float* g, const float* unit, float* out, int64_t n, int
   if (!g || !unit || !out) return fail(NRN_E_INVALID, "nrn_scale_rows: null argument");
   cudaError_t e = nrn::launch_ray_loss_scale(g, unit, out, n, per_row, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_loss_scale_kernel");
+}
+
+int nrn_adam_step(const NrnAdamArgs* a) {
+  if (!a) return fail(NRN_E_INVALID, "nrn_adam_step: null args");
+  if (a->n_blocks < 0 || a->n_tensors < 0) return fail(NRN_E_INVALID, "nrn_adam_step: n_tensors = %d, n_blocks = %d", a->n_tensors, a->n_blocks);
+  if (!a->params || !a->exp_avg || !a->exp_avg_sq || !a->grad_ptrs || !a->blocks || !a->lr || !a->step)
+    return fail(NRN_E_INVALID, "nrn_adam_step: null buffer");
+  if (!(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->eps >= 0.f))
+    return fail(NRN_E_INVALID, "nrn_adam_step: betas / eps out of range");
+  nrn::AdamParams p{};
+  p.params = static_cast<float*>(a->params); p.exp_avg = static_cast<float*>(a->exp_avg); p.exp_avg_sq = static_cast<float*>(a->exp_avg_sq);
+  p.grads = static_cast<const float* const*>(a->grad_ptrs); p.blocks = static_cast<const nrn::AdamBlock*>(a->blocks);
+  p.lr = static_cast<const float*>(a->lr); p.step = static_cast<long long*>(a->step);
+  p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
+  const cudaError_t e = nrn::launch_adam(p, a->n_tensors, a->n_blocks, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "adam_kernel");
 }
 
 int nrn_timing_enable(int on) {

@@ -420,14 +420,30 @@ __global__ void wgrad_reduce_kernel(const WgradParams p, float* __restrict__ ner
     if (slot >= 0) {
       const int nsplit = p.splits[slot];
       const int per = (p.n_tiles + nsplit - 1) / nsplit;
-      for (int sp = 0; sp < nsplit; ++sp) {
-        if (sp * per >= p.n_tiles) break;   // this split owned no tiles: its scratch is unwritten
-        const float* part = p.scratch + static_cast<size_t>(base + sp) * kWgScratchFloats;
-        if (s.bias) sum += part[65536 + s.off];
-        else {
-          sum += part[s.off];
-          if (s.off2 >= 0) sum += part[s.off2];
+      const int n_valid = min(nsplit, (p.n_tiles + per - 1) / per);   // splits beyond that owned no tiles: scratch unwritten
+      const float* __restrict__ src = p.scratch + static_cast<size_t>(base) * kWgScratchFloats + (s.bias ? 65536 + s.off : s.off);
+      const bool has2 = !s.bias && s.off2 >= 0;
+      const int d2 = has2 ? s.off2 - s.off : 0;
+      // fixed summation order (split 0, 1, 2, ...) = deterministic gradients; the loads of 8 splits are in flight together
+      int sp = 0;
+      for (; sp + 8 <= n_valid; sp += 8) {
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float* q = src + static_cast<size_t>(sp + i) * kWgScratchFloats;
+          a[i] = __ldg(q);
+          b[i] = has2 ? __ldg(q + d2) : 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sum += a[i];
+          if (has2) sum += b[i];
+        }
+      }
+      for (; sp < n_valid; ++sp) {
+        const float* q = src + static_cast<size_t>(sp) * kWgScratchFloats;
+        sum += __ldg(q);
+        if (has2) sum += __ldg(q + d2);
       }
     }
   }

@@ -41,8 +41,18 @@ def _ptr_array(tensors):
 # ---------------------------------------------------------------------------------------------
 # weight packing (cached per module, invalidated by the parameters' version counters)
 # ---------------------------------------------------------------------------------------------
+_PARAM_EPOCH = 0   # bumped by optimizers that update parameters behind autograd's back (optim.Adam)
+
+
+def note_parameters_changed() -> None:
+    """Invalidate every cached fp16 weight image: parameters were updated by a kernel that does not touch
+    PyTorch's version counters."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
+
+
 def _versions(params):
-    return tuple((p.data_ptr(), p._version) for p in params)
+    return (_PARAM_EPOCH,) + tuple((p.data_ptr(), p._version) for p in params)
 
 
 def nerf_param_list(net):

@@ -229,7 +229,8 @@ class training_wrapper_class(torch.nn.Module):
         imageid_to_timestepid = self._i2t[1]
         n_rays = rays_o.shape[0]
         timestep = imageid_to_timestepid[batch_pixel_indices[:, 0].to(dev).long()]
-        info = {"ray_bending_latents": latent_table[timestep, :]}                     # [N, Z]
+        # [N, Z]; index_select (backward = one index_add_) instead of advanced indexing (backward = sort-based index_put_)
+        info = {"ray_bending_latents": torch.index_select(latent_table, 0, timestep)}
         detailed = args.offsets_loss_weight > 0.0 or args.divergence_loss_weight > 0.0
         rgb, disp, acc, extras = T.render(rays_o, rays_d, chunk=args.chunk, verbose=i < 10, retraw=True,
                                           additional_pixel_information=info, detailed_output=detailed, **render_kwargs_train)
