@@ -161,14 +161,17 @@ typedef struct NrnDivArgs {
   const float* e;                  /* [P][3] probe vectors ~ N(0, I) (torch.randn_like, run_nerf_helpers.py:110) */
   const float* unmasked_offsets;   /* [P][3] coarse pass output */
   const float* rigidity_mask;      /* [P]    coarse pass output */
-  const float* weights;            /* [P]    1 - exp(-relu(opacity_alpha)), detached (train.py:267) */
+  const float* weights;            /* [P]    1 - exp(-relu(opacity_alpha)), detached (train.py:267) ... */
+  int32_t weights_are_opacity_alpha; /* ... or, if 1, opacity_alpha itself: the kernels apply 1 - exp(-relu(.)) */
   const float* const* net_w;       /* 5: ray_bending.network.i.weight (fp32, reference layout) */
   const float* const* rig_w;       /* 3: ray_bending.rigidity_network.i.weight */
   void* tangent_stash;             /* nrn_div_stash_bytes(): written by forward, read by backward */
   float* d; float* alpha; float* beta; float* tau_c;   /* [P] each: written by forward, read by backward */
   float* loss;                     /* forward out [n_rays]: mean over the ray's samples of weights * d^2 */
   /* backward only */
-  const float* G;                  /* [P] dL/dd = g_ray * 2 * weights * d / n_samples */
+  const float* G;                  /* [P] dL/dd = g_ray * 2 * weights * d / n_samples, or NULL with g_ray / G_workspace: */
+  const float* g_ray;              /* [n_rays] upstream gradient of `loss`; G is then computed into G_workspace [P] */
+  float* G_workspace;
   void* adjoint_stash;             /* workspace, nrn_div_grad_stash_bytes() */
   float* wgrad_scratch;            /* workspace, nrn_wgrad_scratch_bytes() */
   float* d_unmasked_offsets;       /* out [P][3] gradient w.r.t. the coarse unmasked offsets */

@@ -51,10 +51,11 @@ class NrnDivArgs(C.Structure):
     _fields_ = [
         ("n_rays", C.c_int32), ("n_samples", C.c_int32),
         ("stash", _vp), ("e", _vp), ("unmasked_offsets", _vp), ("rigidity_mask", _vp), ("weights", _vp),
+        ("weights_are_opacity_alpha", C.c_int32),
         ("net_w", C.POINTER(_vp)), ("rig_w", C.POINTER(_vp)),
         ("tangent_stash", _vp), ("d", _vp), ("alpha", _vp), ("beta", _vp), ("tau_c", _vp), ("loss", _vp),
-        ("G", _vp), ("adjoint_stash", _vp), ("wgrad_scratch", _vp), ("d_unmasked_offsets", _vp), ("d_rigidity_mask", _vp),
-        ("bender_grad", _vp),
+        ("G", _vp), ("g_ray", _vp), ("G_workspace", _vp), ("adjoint_stash", _vp), ("wgrad_scratch", _vp), ("d_unmasked_offsets", _vp),
+        ("d_rigidity_mask", _vp), ("bender_grad", _vp),
         ("stream", _vp),
     ]
 

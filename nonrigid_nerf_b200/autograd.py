@@ -206,7 +206,7 @@ class _DivergenceFn(torch.autograd.Function):
     """per-ray mean_s(w * (e^T J e)^2) of the offset field, closed-form forward and backward (csrc/div.cu)."""
 
     @staticmethod
-    def forward(ctx, unmasked, rigidity, weights, e, stash, bender, bender_token):
+    def forward(ctx, unmasked, rigidity, weights, e, stash, bender, bender_token, w_is_alpha=False):
         n, s = unmasked.shape[0], unmasked.shape[1]
         dev = unmasked.device
         lib = _lib.load()
@@ -223,6 +223,7 @@ class _DivergenceFn(torch.autograd.Function):
         scal = torch.empty(4, n * s, dtype=torch.float32, device=dev)
         loss = torch.empty(n, dtype=torch.float32, device=dev)
         a.stash, a.e, a.unmasked_offsets, a.rigidity_mask, a.weights = stash.data_ptr(), e.data_ptr(), un.data_ptr(), rg.data_ptr(), w.data_ptr()
+        a.weights_are_opacity_alpha = 1 if w_is_alpha else 0
         a.net_w, a.rig_w = net_arr, rig_arr
         a.tangent_stash = tan.data_ptr()
         a.d, a.alpha, a.beta, a.tau_c = (scal[i].data_ptr() for i in range(4))
@@ -231,6 +232,7 @@ class _DivergenceFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.nrn_divergence_forward(C.byref(a)), "divergence_forward")
         ctx.keep = (un, rg, w, e, stash, tan, scal, bender)
+        ctx.w_is_alpha = bool(w_is_alpha)
         ctx.shape = (n, s)
         ctx.in_shapes = (unmasked.shape, rigidity.shape)
         return loss
@@ -241,19 +243,20 @@ class _DivergenceFn(torch.autograd.Function):
         n, s = ctx.shape
         dev = un.device
         lib = _lib.load()
-        # G = dL/dd per point = g_ray * 2 * w * d / S
-        G = (g.reshape(n, 1).float() * (2.0 / s)) * w.reshape(n, s) * scal[0].reshape(n, s)
-        G = G.contiguous()
+        # G = dL/dd per point = g_ray * 2 * w * d / S, computed (with its max, the loss-scale source) by the library
+        g = g.reshape(n).contiguous().float()
+        G = torch.empty(n * s, dtype=torch.float32, device=dev)
         a = _lib.NrnDivArgs()
         a.n_rays, a.n_samples = n, s
         net_w, _, rig_w, _ = ops.bender_param_list(bender)
         net_arr = ops._ptr_array([t.detach() for t in net_w])
         rig_arr = ops._ptr_array([t.detach() for t in rig_w])
         a.stash, a.e, a.unmasked_offsets, a.rigidity_mask, a.weights = stash.data_ptr(), e.data_ptr(), un.data_ptr(), rg.data_ptr(), w.data_ptr()
+        a.weights_are_opacity_alpha = 1 if ctx.w_is_alpha else 0
         a.net_w, a.rig_w = net_arr, rig_arr
         a.tangent_stash = tan.data_ptr()
         a.d, a.alpha, a.beta, a.tau_c = (scal[i].data_ptr() for i in range(4))
-        a.G = G.data_ptr()
+        a.g_ray, a.G_workspace = g.data_ptr(), G.data_ptr()
         adj = torch.empty(lib.nrn_div_grad_stash_bytes(n, s), dtype=torch.uint8, device=dev)
         scratch = torch.empty(lib.nrn_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
         d_un = torch.empty(n * s, 3, dtype=torch.float32, device=dev)
@@ -265,15 +268,17 @@ class _DivergenceFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.nrn_divergence_backward(C.byref(a)), "divergence_backward")
         ctx.keep = None
-        return (d_un.view(ctx.in_shapes[0]), d_rg.view(ctx.in_shapes[1]), None, None, None, None, bend_grad)
+        return (d_un.view(ctx.in_shapes[0]), d_rg.view(ctx.in_shapes[1]), None, None, None, None, bend_grad, None)
 
 
-def divergence_loss(unmasked: torch.Tensor, rigidity: torch.Tensor, weights: torch.Tensor, bender,
-                    e: Optional[torch.Tensor] = None) -> torch.Tensor:
+def divergence_loss(unmasked: torch.Tensor, rigidity: torch.Tensor, weights: Optional[torch.Tensor], bender,
+                    e: Optional[torch.Tensor] = None, opacity_alpha: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused divergence regulariser on the coarse samples of the LAST differentiable coarse pass.
     unmasked [N,S,3], rigidity [N,S,1] must be that pass's outputs (they locate its activation stash and
     carry the gradient w.r.t. the primal bender evaluation); weights [N,S] are used detached; `e` [N*S,3]
-    are the Hutchinson probes (drawn with torch.randn like run_nerf_helpers.py:110 when None)."""
+    are the Hutchinson probes (drawn with torch.randn like run_nerf_helpers.py:110 when None).
+    Instead of `weights`, `opacity_alpha` [N,S] may be given: the kernels then apply the reference's
+    1 - exp(-relu(opacity_alpha)) (train.py:267) themselves."""
     stash = lookup_stash(unmasked)
     if stash is None:
         raise RuntimeError("nonrigid_nerf_b200: no activation stash for these offsets -- the fused divergence term needs the "
@@ -282,7 +287,9 @@ def divergence_loss(unmasked: torch.Tensor, rigidity: torch.Tensor, weights: tor
     if e is None:
         e = torch.randn(n * s, 3, device=unmasked.device)
     _, bend_p = _flat_params_bender(bender)
-    return _DivergenceFn.apply(unmasked, rigidity, weights, e, stash, bender, _bender_token(bender, bend_p))
+    if opacity_alpha is not None:
+        return _DivergenceFn.apply(unmasked, rigidity, opacity_alpha, e, stash, bender, _bender_token(bender, bend_p), True)
+    return _DivergenceFn.apply(unmasked, rigidity, weights, e, stash, bender, _bender_token(bender, bend_p), False)
 
 
 def _flat_params_bender(bender):

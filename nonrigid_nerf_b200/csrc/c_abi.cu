@@ -326,7 +326,7 @@ static int fill_div(const NrnDivArgs* a, nrn::DivParams& p, const char* who) {
   p.P = static_cast<long long>(a->n_rays) * a->n_samples;
   p.S = a->n_samples; p.n_rays = a->n_rays;
   p.stash = static_cast<const uint8_t*>(a->stash);
-  p.e = a->e; p.unmasked = a->unmasked_offsets; p.rigidity = a->rigidity_mask; p.w = a->weights;
+  p.e = a->e; p.unmasked = a->unmasked_offsets; p.rigidity = a->rigidity_mask; p.w = a->weights; p.w_is_alpha = a->weights_are_opacity_alpha != 0;
   for (int i = 0; i < 5; ++i) { if (!a->net_w[i]) return fail(NRN_E_INVALID, "%s: null weight", who); p.net_w[i] = a->net_w[i]; }
   for (int i = 0; i < 3; ++i) { if (!a->rig_w[i]) return fail(NRN_E_INVALID, "%s: null weight", who); p.rig_w[i] = a->rig_w[i]; }
   p.tan = static_cast<uint8_t*>(a->tangent_stash);
@@ -351,16 +351,17 @@ int nrn_divergence_backward(const NrnDivArgs* a) {
   nrn::DivParams p{};
   int rc = fill_div(a, p, "nrn_divergence_backward");
   if (rc) return rc;
-  if (!a->G || !a->adjoint_stash || !a->wgrad_scratch || !a->d_unmasked_offsets || !a->d_rigidity_mask || !a->bender_grad)
+  if ((!a->G && !(a->g_ray && a->G_workspace)) || !a->adjoint_stash || !a->wgrad_scratch || !a->d_unmasked_offsets || !a->d_rigidity_mask ||
+      !a->bender_grad)
     return fail(NRN_E_INVALID, "nrn_divergence_backward: null argument");
   DeviceState* ds;
   rc = device_state(&ds);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(a->stream);
   float* amax = reinterpret_cast<float*>(ds->err_word + 2);
-  p.G = a->G; p.amax = amax; p.adj = static_cast<uint8_t*>(a->adjoint_stash);
+  p.G = a->G ? a->G : a->G_workspace; p.amax = amax; p.adj = static_cast<uint8_t*>(a->adjoint_stash);
   p.d_unmasked = a->d_unmasked_offsets; p.d_rigid = a->d_rigidity_mask;
-  cudaError_t e = nrn::launch_absmax(a->G, p.P, amax, st);
+  cudaError_t e = a->G ? nrn::launch_absmax(a->G, p.P, amax, st) : nrn::launch_div_G(p, a->g_ray, a->G_workspace, amax, st);
   if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
   { ScopedTimer tm(5, st); e = nrn::launch_div_bwd(p, st); }
   if (e != cudaSuccess) return cuda_fail(e, "div_bwd_kernel");

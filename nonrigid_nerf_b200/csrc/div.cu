@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kDivThreads) div_fwd_kernel(const DivParams p)
     for (int d = 0; d < 3; ++d) { e[d] = p.e[pt * 3 + d]; off[d] = p.unmasked[pt * 3 + d]; }
     r = p.rigidity[pt];
     w = p.w[pt];
+    if (p.w_is_alpha) w = 1.0f - expf(-fmaxf(w, 0.f));
   }
   // e image (bender-input layout: hi columns 0-2, lo columns 3-5)
   {
@@ -273,6 +274,31 @@ __global__ void __launch_bounds__(kDivThreads) div_bwd_kernel(const DivParams p)
 
 // ------------------------------------------------------------------------------------------------
 static size_t div_smem() { return sizeof(float) * (kWTotal + kActFloats); }
+
+namespace {
+__global__ void div_G_kernel(const DivParams p, const float* __restrict__ g_ray, float* __restrict__ G, float* __restrict__ amax) {
+  const long long pt = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  float v = 0.f;
+  if (pt < p.P) {
+    float w = p.w[pt];
+    if (p.w_is_alpha) w = 1.0f - expf(-fmaxf(w, 0.f));
+    v = g_ray[pt / p.S] * (2.0f / static_cast<float>(p.S)) * w * p.d[pt];
+    G[pt] = v;
+  }
+  float m = fabsf(v);
+  if (!(m < 3.0e38f)) m = 0.f;   // ignore inf / nan: the scale must stay finite
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));   // non-negative floats order like ints
+}
+}  // namespace
+
+cudaError_t launch_div_G(const DivParams& p, const float* g_ray, float* G, float* amax, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float), st);
+  if (e != cudaSuccess || p.P <= 0) return e;
+  div_G_kernel<<<static_cast<unsigned>((p.P + 255) / 256), 256, 0, st>>>(p, g_ray, G, amax);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_div_fwd(const DivParams& p, cudaStream_t st) {
   const long long tiles = (p.P + kTileM - 1) / kTileM;

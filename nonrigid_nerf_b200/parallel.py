@@ -244,8 +244,9 @@ class training_wrapper_class(torch.nn.Module):
                             args.offsets_loss_weight * sched if use_offsets else 0.0, args.rigidity_loss_weight)
         if self.ray_bender is not None and args.divergence_loss_weight > 0.0:
             # exact_divergence = False, backprop_into_weights = False (train.py:246-247); fused closed-form kernel
-            w = 1.0 - torch.exp(-F.relu(extras["opacity_alpha"].detach()))
-            div = _ag.divergence_loss(extras["unmasked_offsets"], extras["rigidity_mask"], w, self.ray_bender)
+            # weights 1 - exp(-relu(opacity_alpha)) (train.py:267) are formed inside the kernels
+            div = _ag.divergence_loss(extras["unmasked_offsets"], extras["rigidity_mask"], None, self.ray_bender,
+                                      opacity_alpha=extras["opacity_alpha"])
             loss = loss + args.divergence_loss_weight * sched * div
         return loss
 

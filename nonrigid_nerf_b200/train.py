@@ -92,16 +92,39 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
 
     rnd = dummy_kwargs.get("randomness", None)
 
+    # The reference draws t_rand, the coarse noise, u and the fine noise with four generator calls
+    # (train.py:861, 744, 915).  Here one torch.rand and one torch.randn fill a pool per call of render_rays and the
+    # four arrays are contiguous slices of it: same distributions, two launches instead of four (+ two scalings).
+    n_fine = N_samples + N_importance
+    want = {"t_rand": (torch.rand, n * N_samples if perturb > 0.0 else 0),
+            "u": (torch.rand, n * N_importance if (perturb > 0.0 and N_importance > 0) else 0),
+            "noise_c": (torch.randn, n * N_samples if raw_noise_std > 0.0 else 0),
+            "noise_f": (torch.randn, n * n_fine if (raw_noise_std > 0.0 and N_importance > 0) else 0)}
+    pools = {}
+    if rnd is None:
+        for fn in (torch.rand, torch.randn):
+            tot = sum(cnt for f, cnt in want.values() if f is fn)
+            if tot:
+                buf = fn(tot, device=dev)
+                if fn is torch.randn and raw_noise_std != 1.0:
+                    buf = buf * raw_noise_std
+                o = 0
+                for k, (f, cnt) in want.items():
+                    if f is fn and cnt:
+                        pools[k] = buf[o:o + cnt]
+                        o += cnt
+
     def draw(key, fn, *shape):
         if rnd is not None:
-            return rnd[key].to(dev)
-        return fn(*shape, device=dev)
+            t = rnd[key].to(dev)
+            return t * raw_noise_std if (fn is torch.randn and raw_noise_std != 1.0) else t
+        return pools[key].view(*shape)
 
     # coarse depths (train.py:847-869); t_rand drawn first, like the reference
     t_rand = draw("t_rand", torch.rand, n, N_samples) if perturb > 0.0 else None
     z_vals = ops.sample_coarse(rays, N_samples, t_rand, lindisp)
     raw, details = _ag.field(network_fn, rays, z_vals, latents, detailed_output)
-    noise = draw("noise_c", torch.randn, n, N_samples) * raw_noise_std if raw_noise_std > 0.0 else None
+    noise = draw("noise_c", torch.randn, n, N_samples) if raw_noise_std > 0.0 else None   # already scaled by raw_noise_std
 
     if N_importance > 0:
         u = draw("u", torch.rand, n, N_importance) if perturb > 0.0 else None   # det=(perturb == 0), train.py:915
@@ -109,7 +132,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         z_fine = c0["z_vals_out"]   # sorted union, detached (train.py:918-920)
         run_fn = network_fn if network_fine is None else network_fine
         raw, fine_details = _ag.field(run_fn, rays, z_fine, latents, detailed_output)
-        noise_f = draw("noise_f", torch.randn, n, N_samples + N_importance) * raw_noise_std if raw_noise_std > 0.0 else None
+        noise_f = draw("noise_f", torch.randn, n, n_fine) if raw_noise_std > 0.0 else None
         c1 = _ag.composite(raw, z_fine, rays_d, noise_f, white_bkgd)
     else:
         c0 = None
