@@ -41,13 +41,28 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const AdamParams a) 
   float* __restrict__ p = a.params + b.flat_off;
   float* __restrict__ m = a.exp_avg + b.flat_off;
   float* __restrict__ v = a.exp_avg_sq + b.flat_off;
-  for (int i = threadIdx.x; i < b.count; i += kAdamThreads) {
-    const float gi = g[i];
-    const float mi = m[i] + (gi - m[i]) * w1;
-    const float vi = a.beta2 * v[i] + w2 * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + a.eps));
+  // 8 elements per thread: all loads first (the kernel is a latency-bound stream over 4 arrays)
+  constexpr int kPer = kAdamBlockElems / kAdamThreads;
+  float gi[kPer], mi[kPer], vi[kPer], pi[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int i = threadIdx.x + k * kAdamThreads;
+    const bool in = i < b.count;
+    gi[k] = in ? g[i] : 0.f;
+    mi[k] = in ? m[i] : 0.f;
+    vi[k] = in ? v[i] : 0.f;
+    pi[k] = in ? p[i] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int i = threadIdx.x + k * kAdamThreads;
+    if (i < b.count) {
+      const float mk = mi[k] + (gi[k] - mi[k]) * w1;
+      const float vk = a.beta2 * vi[k] + w2 * gi[k] * gi[k];
+      m[i] = mk;
+      v[i] = vk;
+      p[i] = pi[k] - step_size * (mk / (sqrtf(vk) / bc2_sqrt + a.eps));
+    }
   }
 }
 }  // namespace

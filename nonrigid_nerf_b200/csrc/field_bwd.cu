@@ -308,6 +308,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
         }
       };
 
+      // The ReLU masks come from the forward stash (read once, straight from HBM).  One thread pulls the image the
+      // NEXT step will read into L2 while this step's epilogue runs, so the per-thread loads find it there.
+      const uint8_t* st_tile = p.stash + tile * kStashTileBytes;
+      auto prefetch = [&](uint32_t off, uint32_t bytes) {
+        if (wg_leader) {
+          for (uint32_t o = 0; o < bytes; o += 16384u) tma_prefetch_l2(st_tile + off + o, bytes - o < 16384u ? bytes - o : 16384u);
+        }
+      };
+      prefetch(kStH + 7 * kHBytes, kHBytes);
       // ---- d_raw image: [g_r g_g g_b g_sigma 0 ...] (K = 16) ----
       {
         float g[4] = {0.f, 0.f, 0.f, 0.f};
@@ -329,6 +338,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
 #pragma unroll 1
       for (int s = 0; s < 3; ++s) {
         wait_acc(300 + s);
+        if (s < 2) prefetch(kStH + (6 - s) * kHBytes, kHBytes); else prefetch(kStE, kEBytes);
         stash_begin();
         epi_mask_store<256>(taddr, st + kStH + (7 - s) * kHBytes, a_row);
         stash_store(kGsY + (7 - s) * kHBytes, kHBytes);
@@ -336,12 +346,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
       }
       // ---- L5e^T: gradient into the skip-connected embedding ----
       wait_acc(303);
+      prefetch(kStH + 4 * kHBytes, kHBytes);
       pe_backward(taddr, st + kStE, dx);
       signal_ready();   // A operand (dY5) untouched; accumulator drained
       // ---- L5h^T, L4^T .. L1^T : dY4 .. dY0 ----
 #pragma unroll 1
       for (int s = 0; s < 5; ++s) {
         wait_acc(304 + s);
+        if (s < 4) prefetch(kStH + (3 - s) * kHBytes, kHBytes); else prefetch(kStE, kEBytes);
         stash_begin();
         epi_mask_store<256>(taddr, st + kStH + (4 - s) * kHBytes, a_row);
         stash_store(kGsY + (4 - s) * kHBytes, kHBytes);
@@ -349,6 +361,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
       }
       // ---- L0^T: gradient into the embedding; then through the bend ----
       wait_acc(309);
+      if (HAS_BENDER) prefetch(kStHb4, 8 * kChunkBytes);
       pe_backward(taddr, st + kStE, dx);
       if (!HAS_BENDER) continue;   // xyz has no learnable upstream without a bender (appendix C)
 
@@ -387,12 +400,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
       signal_ready();
       // ---- B4^T -> dYb3 ----
       wait_acc(310);
+      prefetch(kStHb3, 8 * kChunkBytes);
       stash_begin();
       epi_mask_store<64>(taddr, st + kStHb4, a_row);
       stash_store(kGsYb3, 8 * kChunkBytes);
       signal_ready();
       // ---- B3^T -> dYb2 = [dh * mask (64) | d rigidity pre-activation | 0 (15)] ----
       wait_acc(311);
+      prefetch(kStHb2, 12 * kChunkBytes);
       stash_begin();
       epi_mask_store<64>(taddr, st + kStHb3, a_row);
       {
@@ -405,6 +420,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
       signal_ready();
       // ---- B2^T -> dYb1, B1^T -> dYb0 ----
       wait_acc(312);
+      prefetch(kStHb1, 12 * kChunkBytes);
       stash_begin();
       epi_mask_store<96>(taddr, st + kStHb2, a_row);
       stash_store(kGsYb1, 12 * kChunkBytes);

@@ -97,6 +97,10 @@ __device__ __forceinline__ void tma_bulk_s2g(void* gmem_dst, const void* smem_sr
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// pull a contiguous global range into L2 ahead of the loads that will use it (no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_bulk_wait_read() {
