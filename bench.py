@@ -55,12 +55,14 @@ def synth_batch(rs, n, n_images=86):
 
 
 def read_peaks():
+    """(sustained bf16 TFLOP/s, HBM GB/s, source).  Sustained figures: the kernels are timed inside a long step."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)"
-    return 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        return (float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), float(d.get("hbm_gbs", 6500.0)),
+                "measured (MEASURED_PEAKS.json: sustained bf16 cuBLAS, copy bandwidth)")
+    return 1400.0, 6500.0, "fallback (B200_PROFILING.md figures)"
 
 
 class ClockSampler:
@@ -334,21 +336,35 @@ def main():
 
     value = n_global * args.steps / (ms_total * 1e-3)
     e2e_value = n_global * args.steps / (ms_e2e * 1e-3)
-    peak, peak_src = read_peaks()
-    # dominant kernel kind over the timed region (this rank), algorithmic FLOPs = points x 1,016,320 per launch pair
-    # launches per step of each kind: 2 (coarse + fine pass).  Eager: events of every step were recorded;
-    # graph replay: the captured event pairs hold the timestamps of the last replay of the timed region.
-    per_step = {k: (kinds[k][0] / (kinds[k][1] / 2.0) if kinds[k][1] else 0.0) for k in kinds}
+    peak_tf, peak_gbs, peak_src = read_peaks()
+    # Per-step time of each kernel kind from the instrumented pass (this rank).  Launches per step: field forward /
+    # DGRAD / composite / composite backward 2 (coarse + fine pass), divergence 2 (forward + backward), WGRAD 3 (fine,
+    # coarse, divergence; each followed by its split reduction, timed with it).  Eager: the events of every step
+    # were recorded; graph replay: the captured event pairs hold the timestamps of the last replay.
+    launches = {"wgrad": 3}
+    per_step = {k: (kinds[k][0] / (kinds[k][1] / float(launches.get(k, 2))) if kinds[k][1] else 0.0) for k in kinds}
     dom = max(("field_fwd", "field_dgrad", "wgrad"), key=lambda k: per_step[k])
     dom_ms_per_step = per_step[dom]
-    flops_per_step = args.n_rand * POINTS_PER_RAY * FLOP_PER_POINT
-    achieved = flops_per_step / (dom_ms_per_step * 1e-3) / 1e12
-    # DRAM bytes of that kernel kind (coarse + fine launch), from the committed `ncu --set full` capture of this workload
+    tiles = args.n_rand * POINTS_PER_RAY // 128
+    if dom == "wgrad":
+        # HBM-bound by construction: every stash byte is read once and feeds 256 MACs.
+        alg = tiles * (634880 + 618496) + (args.n_rand * N_SAMPLES // 128) * (94208 + 90112)
+        roof = {"bound": "hbm", "kernel": dom, "achieved": alg / (dom_ms_per_step * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "note": "algorithmic bytes per step = tiles x (634,880 + 618,496) B of stash reads (+ 184,320 B per coarse tile for the "
+                        "divergence term); the time includes the three split reductions"}
+    else:
+        alg = args.n_rand * POINTS_PER_RAY * FLOP_PER_POINT
+        roof = {"bound": "tensor", "kernel": dom, "achieved": alg / (dom_ms_per_step * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                "note": "algorithmic FLOPs per step of this kernel kind (coarse + fine launch) = N_rand x 192 x 1,016,320"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    # DRAM bytes of that kernel kind per step, from the committed `ncu --set full` capture of this workload
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.n_rand == N_RAND:
         with open(tpath) as f:
             traffic = json.load(f).get(dom)
+    roof["traffic"] = traffic
+    roof["peak_source"] = peak_src
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -363,9 +379,7 @@ def main():
         # 1 ray loss + 4 scalings, 3 divergence, 2 composite backwards, 2 absmax, 2 field DGRADs, 3 WGRADs + 3 reductions, 2 optimizer
         "kernel_ms_per_step": per_step, "ms_per_step_instrumented": ms_instrumented / args.steps,
         "cuda_graph": graphed is not None,
-        "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "note": "algorithmic FLOPs per step of this kernel kind (coarse + fine launch) = N_rand x 192 x 1,016,320"},
+        "roofline": roof,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:

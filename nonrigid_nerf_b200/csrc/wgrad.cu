@@ -7,9 +7,12 @@
 // DGRAD (gradient stash) kernels; read MN-major they are exactly the transposed operands WGRAD needs
 // (sm100_ptx.cuh), so no transpose pass exists.  The contraction runs over points (K = 128 per tile).
 //
-// Decomposition: a fixed list of jobs; a job is a set of up to three "sub-MMAs" that share one
-// shared-memory stage (jobs 0-9: one NeRF layer, two 128-row halves of dW; jobs 10-11: the five small
-// ray-bender layers grouped so that every job moves 40-64 KB per stage).  Every job is split over
+// Decomposition: a fixed list of jobs; a job is a set of up to three "sub-MMAs" over one gradient image block (A)
+// and one activation image block (B) per tile (jobs 0-9: one NeRF layer, two 128-row halves of dW; jobs 10-11: the
+// five small ray-bender layers, grouped so that their images are one contiguous range of each stash).  A pipeline
+// stage holds ONE whole 128-point block, A and B alternating through a 3 x 64 KB ring, so every tile is fetched with
+// a handful of 16 KB bulk copies (the first version streamed 64-point halves as 128 one-KB copies per tile and
+// topped out at half the HBM bandwidth).  Every job is split over
 // contiguous tile ranges ("split-K") proportionally to its bytes; partial sums go to a scratch buffer
 // and a second kernel reduces them in a fixed order (deterministic) while un-padding / un-permuting
 // into the reference's parameter layout and dividing out the loss scale.
@@ -28,23 +31,19 @@ namespace {
 
 constexpr long long kWaitLimitCycles = 1ll << 28;
 constexpr int kWgStages = 3;
-constexpr int kSubRows = 64;                       // points per pipeline stage
-constexpr int kSubChunk = kSubRows * 16;           // 1 KB per chunk of a 64-row sub-image
-constexpr int kStageBytes = 64 * kSubChunk;        // up to 64 chunks (A images first, then B images)
+constexpr int kStageBytes = 32 * kChunkBytes;      // one block of up to 32 chunk images (128 points x 8 features each)
 constexpr int kWgThreads = 320;                    // producer, mma, 8 bias/drain warps
 
 struct Sub {
-  int a_chunk, b_chunk, n, tmem_col;  // operand chunk offsets inside the stage, N, accumulator column
+  int a_chunk, b_chunk, n, tmem_col;  // operand chunk offsets inside the A / B stage, N, accumulator column
   int a_cols;                         // valid rows of the 128-row accumulator
 };
 struct Job {
-  int n_imgs;            // number of (A,B) image pairs streamed per stage
-  int a_off[3], a_chunks[3];
-  int b_off[3], b_chunks[3];
+  int a_off, a_chunks;   // contiguous range of the gradient stash tile (bytes, chunks)
+  int b_off, b_chunks;   // contiguous range of the activation stash tile
   int n_sub;
   Sub sub[3];
   int bias;              // compute column sums over all A chunks
-  int a_total, b_total;  // chunks
 };
 
 // job ids: 0 head, 1..7 = L1..L7 (input h_l), 8 L5e, 9 L0, 10 = {B4,B3,B2}, 11 = {B1,B0}
@@ -56,35 +55,31 @@ __device__ __forceinline__ Job job_desc(int j, int compact) {
     else if (j == 8) { a_off = kGsY + 5 * kHBytes; a_cols = 256; b_off = kStE; b_cols = 64; bias = 0; }
     else if (j == 9) { a_off = kGsY; a_cols = 256; b_off = kStE; b_cols = 64; }
     else { a_off = kGsY + j * kHBytes; a_cols = 256; b_off = kStH + (j - 1) * kHBytes; b_cols = 256; }
-    jb.n_imgs = 1;
-    jb.a_off[0] = a_off; jb.a_chunks[0] = a_cols / 8; jb.b_off[0] = b_off; jb.b_chunks[0] = b_cols / 8;
-    jb.a_total = a_cols / 8; jb.b_total = b_cols / 8;
+    jb.a_off = a_off; jb.a_chunks = a_cols / 8; jb.b_off = b_off; jb.b_chunks = b_cols / 8;
     jb.n_sub = a_cols > 128 ? 2 : 1;
-    jb.sub[0] = {0, jb.a_total, b_cols, 0, a_cols > 128 ? 128 : a_cols};
-    jb.sub[1] = {16, jb.a_total, b_cols, 256, 128};
+    jb.sub[0] = {0, 0, b_cols, 0, a_cols > 128 ? 128 : a_cols};
+    jb.sub[1] = {16, 0, b_cols, 256, 128};
     jb.bias = bias;
     return jb;
   }
-  // bender jobs; in compact mode the stashes hold only the bender images
+  // bender jobs: the images of a job are adjacent in both stashes (nrn_common.cuh); in compact mode the stashes hold
+  // only the bender images
   const int ga = compact ? kGsYb4 : 0, sa = compact ? kStBin : 0;
   if (j == 10) {
-    jb.n_imgs = 3;
-    jb.a_off[0] = kGsYb4 - ga; jb.a_chunks[0] = 2;  jb.b_off[0] = kStHb4 - sa; jb.b_chunks[0] = 8;
-    jb.a_off[1] = kGsYb3 - ga; jb.a_chunks[1] = 8;  jb.b_off[1] = kStHb3 - sa; jb.b_chunks[1] = 8;
-    jb.a_off[2] = kGsYb2 - ga; jb.a_chunks[2] = 10; jb.b_off[2] = kStHb2 - sa; jb.b_chunks[2] = 12;
-    jb.a_total = 20; jb.b_total = 28;
+    // A: Yb4 (2 chunks) Yb3 (8) Yb2 (10)      B: Hb2 (12) Hb3 (8) Hb4 (8)
+    jb.a_off = kGsYb4 - ga; jb.a_chunks = 20;
+    jb.b_off = kStHb2 - sa; jb.b_chunks = 28;
     jb.n_sub = 3;
-    jb.sub[0] = {0, 20, 64, 0, 16};
-    jb.sub[1] = {2, 28, 64, 64, 64};
-    jb.sub[2] = {10, 36, 96, 128, 80};
+    jb.sub[0] = {0, 20, 64, 0, 16};      // dYb4 x Hb4
+    jb.sub[1] = {2, 12, 64, 64, 64};     // dYb3 x Hb3
+    jb.sub[2] = {10, 0, 96, 128, 80};    // dYb2 x Hb2
   } else {
-    jb.n_imgs = 2;
-    jb.a_off[0] = kGsYb1 - ga; jb.a_chunks[0] = 12; jb.b_off[0] = kStHb1 - sa; jb.b_chunks[0] = 12;
-    jb.a_off[1] = kGsYb0 - ga; jb.a_chunks[1] = 12; jb.b_off[1] = kStBin - sa; jb.b_chunks[1] = 6;
-    jb.a_total = 24; jb.b_total = 18;
+    // A: Yb1 (12) Yb0 (12)                    B: bender input (6) Hb1 (12)
+    jb.a_off = kGsYb1 - ga; jb.a_chunks = 24;
+    jb.b_off = kStBin - sa; jb.b_chunks = 18;
     jb.n_sub = 2;
-    jb.sub[0] = {0, 24, 96, 0, 96};
-    jb.sub[1] = {12, 36, 48, 96, 96};
+    jb.sub[0] = {0, 6, 96, 0, 96};       // dYb1 x Hb1
+    jb.sub[1] = {12, 0, 48, 96, 96};     // dYb0 x bender input
   }
   jb.bias = compact ? 0 : 1;   // the tangent chain of the divergence term has no bias
   return jb;
@@ -147,7 +142,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
   const int per = (p.n_tiles + nsplit - 1) / nsplit;
   const int t_begin = have ? min(split * per, p.n_tiles) : 0;
   const int t_end = have ? min(t_begin + per, p.n_tiles) : 0;
-  const int n_stages_total = (t_end - t_begin) * 2;   // two 64-row sub-stages per tile
+  const int n_stages_total = (t_end - t_begin) * 2;   // per tile: the A block, then the B block
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
@@ -169,71 +164,65 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
   const Waiter W{&sh->abort_flag, p.err};
 
   if (warp == 0) {
-    // ===================== producer: 64-row sub-images of dY and X =====================
-    // all 32 lanes issue bulk copies (1 KB chunk each): a single lane issuing up to 64 copies per stage
-    // would be the bottleneck of this HBM-bound kernel
-    uint32_t stage = 0, phase = 0;
-    for (int it = 0; it < n_stages_total; ++it) {
-      const long long tile = t_begin + (it >> 1);
-      const int sub = it & 1;
-      if (lane == 0) {
+    // ===================== producer: whole image blocks, 16 KB bulk copies =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < n_stages_total; ++it) {
+        const long long tile = t_begin + (it >> 1);
+        const bool is_b = (it & 1) != 0;
+        const uint8_t* src = is_b ? p.stash + tile * p.stash_tile_bytes + jb.b_off : p.gstash + tile * p.gstash_tile_bytes + jb.a_off;
+        const uint32_t bytes = static_cast<uint32_t>(is_b ? jb.b_chunks : jb.a_chunks) * kChunkBytes;
         W.wait(&sh->empty[stage], phase ^ 1u, 101);
-        mbar_arrive_expect_tx(&sh->full[stage], (jb.a_total + jb.b_total) * kSubChunk);
+        mbar_arrive_expect_tx(&sh->full[stage], bytes);
+        uint8_t* dst = smem + stage * kStageBytes;
+        for (uint32_t o = 0; o < bytes; o += 16384u) tma_bulk_g2s(dst + o, src + o, bytes - o < 16384u ? bytes - o : 16384u, &sh->full[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      uint8_t* dst = smem + stage * kStageBytes;
-      const uint8_t* ga = p.gstash + tile * p.gstash_tile_bytes + sub * kSubChunk;
-      const uint8_t* gb = p.stash + tile * p.stash_tile_bytes + sub * kSubChunk;
-      int ca = 0, cb = jb.a_total;
-      for (int im = 0; im < jb.n_imgs; ++im) {
-        if (lane < jb.a_chunks[im])
-          tma_bulk_g2s(dst + (ca + lane) * kSubChunk, ga + jb.a_off[im] + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
-        if (lane < jb.b_chunks[im])
-          tma_bulk_g2s(dst + (cb + lane) * kSubChunk, gb + jb.b_off[im] + lane * kChunkBytes, kSubChunk, &sh->full[stage]);
-        ca += jb.a_chunks[im];
-        cb += jb.b_chunks[im];
-      }
-      if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < n_stages_total; ++it) {
-        W.wait(&sh->full[stage], phase, 201);
+      for (int it = 0; it < n_stages_total; it += 2) {
+        const uint32_t sa = stage;
+        W.wait(&sh->full[sa], phase, 201);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        const uint32_t sb = stage;
+        W.wait(&sh->full[sb], phase, 202);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
         tc_fence_after_sync();
-        const uint32_t s0 = smem_u32(smem + stage * kStageBytes);
+        const uint32_t a0 = smem_u32(smem + sa * kStageBytes), b0 = smem_u32(smem + sb * kStageBytes);
         for (int s = 0; s < jb.n_sub; ++s) {
-          const Sub sb = jb.sub[s];
-          const uint32_t idesc = umma_instr_desc(128, sb.n, UMMA_F16, UMMA_F16, UMMA_MN_MAJOR, UMMA_MN_MAJOR);
+          const Sub sb_ = jb.sub[s];
+          const uint32_t idesc = umma_instr_desc(128, sb_.n, UMMA_F16, UMMA_F16, UMMA_MN_MAJOR, UMMA_MN_MAJOR);
           // MN-major: SBO = stride between 8-feature chunks, LBO = stride between 8-point groups
-          const uint64_t adesc = umma_smem_desc(s0 + sb.a_chunk * kSubChunk, 128, kSubChunk);
-          const uint64_t bdesc = umma_smem_desc(s0 + sb.b_chunk * kSubChunk, 128, kSubChunk);
-          for (int k = 0; k < kSubRows / 16; ++k) {
-            umma_f16_ss(tmem_base + sb.tmem_col, umma_desc_advance(adesc, k * 256), umma_desc_advance(bdesc, k * 256), idesc,
+          const uint64_t adesc = umma_smem_desc(a0 + sb_.a_chunk * kChunkBytes, 128, kChunkBytes);
+          const uint64_t bdesc = umma_smem_desc(b0 + sb_.b_chunk * kChunkBytes, 128, kChunkBytes);
+          for (int k = 0; k < kTileM / 16; ++k) {
+            umma_f16_ss(tmem_base + sb_.tmem_col, umma_desc_advance(adesc, k * 256), umma_desc_advance(bdesc, k * 256), idesc,
                         (it | k) ? 1u : 0u);
           }
         }
-        umma_commit(&sh->empty[stage]);
-        if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        umma_commit(&sh->empty[sa]);
+        umma_commit(&sh->empty[sb]);
       }
       umma_commit(&sh->done);
     }
   } else {
     // ===================== bias column sums (8 warps), then accumulator drain =====================
     const int t = threadIdx.x - 64;           // 0..255
-    const int c = t >> 3, g = t & 7;          // chunk, row group
+    const int c = t >> 3, g = t & 7;          // chunk, group of 16 points
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < n_stages_total; ++it) {
       W.wait(&sh->full[stage], phase, 301);
-      if (jb.bias) {   // warp-uniform; lanes whose chunk lies beyond the A images contribute zeros
-        const bool live = c < jb.a_total;
-        const uint8_t* src = smem + stage * kStageBytes + c * kSubChunk + g * 8 * 16;
+      if (jb.bias && (it & 1) == 0) {   // warp-uniform; an A stage.  Lanes whose chunk lies beyond the block contribute zeros
+        const bool live = c < jb.a_chunks;
+        const uint8_t* src = smem + stage * kStageBytes + c * kChunkBytes + g * 16 * 16;
         float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (live) {
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
+          for (int r = 0; r < 16; ++r) {
             const uint4 w = *reinterpret_cast<const uint4*>(src + r * 16);
             const __half2* h = reinterpret_cast<const __half2*>(&w);
 #pragma unroll
@@ -256,7 +245,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
       if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
     float* part = p.scratch + static_cast<size_t>(blockIdx.x) * kWgScratchFloats;
-    if (have && jb.bias && g == 0 && c < jb.a_total) {
+    if (have && jb.bias && g == 0 && c < jb.a_chunks) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) part[65536 + c * 8 + q] = acc[q];
     }
