@@ -41,6 +41,11 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
     a = _lib.NrnCompositeArgs()
     a.n_rays, a.n_samples, a.channels = 4, 64, 3
     assert lib.nrn_composite(ctypes.byref(a)) == -1
+    assert lib.nrn_adam_step(None) == -1 and b"null args" in lib.nrn_last_error()
+    ad = _lib.NrnAdamArgs()
+    ad.n_tensors, ad.n_blocks = 3, 4
+    assert lib.nrn_adam_step(ctypes.byref(ad)) == -1 and b"null buffer" in lib.nrn_last_error()
+    assert lib.nrn_divergence_backward(None) == -1
     with pytest.raises(RuntimeError):
         _lib.check(-1, "unit test")
 
@@ -85,6 +90,11 @@ def test_unsupported_configurations_raise_loudly():
         T.render(o, d, ndc=False, additional_pixel_information={"ray_bending_latents": torch.zeros(4, 32)})
     with pytest.raises(RuntimeError, match="pytest"):
         T.raw2outputs(torch.zeros(2, 4, 5), torch.zeros(2, 4), torch.ones(2, 3), pytest=True)
+    from nonrigid_nerf_b200 import optim
+    with pytest.raises(RuntimeError, match="CUDA"):
+        optim.Adam([torch.zeros(3, requires_grad=True)], lr=1e-3)          # no CPU path
+    with pytest.raises(RuntimeError, match="flat list"):
+        optim.Adam([{"params": [torch.zeros(3, requires_grad=True)]}], lr=1e-3)
 
 
 def test_shard_bounds_follow_dataparallel_chunking():
