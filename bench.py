@@ -375,7 +375,7 @@ def main():
                    "l2": "per-step working set (activation + gradient stash ~1.9 GB) exceeds the 126 MB L2; 8 rotating input batches"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(sum(a.nbytes for a in host[0])),
                 "d2h_bytes_per_step": 4},
-        "gpu_launches": 33 * args.steps,   # this repo's kernels per step: 6 weight packs, 1 coarse sampler, 2 field forwards, 2 composites,
+        "gpu_launches": 30 * args.steps,   # this repo's kernels per step: 3 weight packs, 1 coarse sampler, 2 field forwards, 2 composites,
         # 1 ray loss + 4 scalings, 3 divergence, 2 composite backwards, 2 absmax, 2 field DGRADs, 3 WGRADs + 3 reductions, 2 optimizer
         "kernel_ms_per_step": per_step, "ms_per_step_instrumented": ms_instrumented / args.steps,
         "cuda_graph": graphed is not None,

@@ -138,9 +138,7 @@ int nrn_pack_nerf(const float* const* w, const float* const* b, int input_ch, in
     src.b[i] = b[i];
   }
   cudaError_t e = nrn::launch_pack_nerf(src, input_ch, out_ch, packed, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return cuda_fail(e, "pack_nerf_kernel");
-  e = nrn::launch_pack_nerf_t(src, input_ch, out_ch, static_cast<uint8_t*>(packed) + nrn::kNerfTOffset, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_nerf_t_kernel");
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_nerf_kernel");
 }
 
 int nrn_pack_bender(const float* const* net_w, const float* const* net_b, const float* const* rig_w,
@@ -153,9 +151,7 @@ int nrn_pack_bender(const float* const* net_w, const float* const* net_b, const 
   for (int i = 0; i < 4; ++i) src.net_b[i] = net_b[i];
   for (int i = 0; i < 3; ++i) { src.rig_w[i] = rig_w[i]; src.rig_b[i] = rig_b[i]; }
   cudaError_t e = nrn::launch_pack_bender(src, packed, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return cuda_fail(e, "pack_bender_kernel");
-  e = nrn::launch_pack_bender_t(src, static_cast<uint8_t*>(packed) + nrn::kBendTOffset, static_cast<cudaStream_t>(stream));
-  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_bender_t_kernel");
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_bender_kernel");
 }
 
 int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_samples, int lindisp, float* z_vals,

@@ -81,7 +81,7 @@ constexpr int kAdjTileBytes = kGradTileBytes - kGsYb4;     // 90,112: adjoints o
 
 // ------------------------------------------------------------------------------------------
 // Transposed weight images for DGRAD (dX = dY . W: B operand = W^T, rows = input features,
-// K = output features), fp16, in the order field_bwd.cu streams them (pack_t.cu):
+// K = output features), fp16, in the order field_bwd.cu streams them (pack.cu):
 //   head^T [2 chunks][256][8] | L7^T L6^T [32][256][8] | L5e^T [32][64][8] | L5h^T L4^T..L1^T | L0^T [32][64][8]
 //   bender: B4^T [2][64][8] | B3^T [8][64][8] | B2^T [10][96][8] | B1^T [12][96][8] | B0^T [12][48][8]
 // ------------------------------------------------------------------------------------------

@@ -17,7 +17,5 @@ struct BenderSrc {
 
 cudaError_t launch_pack_nerf(const NerfSrc& src, int in_ch, int out_ch, void* packed, cudaStream_t st);
 cudaError_t launch_pack_bender(const BenderSrc& src, void* packed, cudaStream_t st);
-cudaError_t launch_pack_nerf_t(const NerfSrc& src, int in_ch, int out_ch, void* packed_t, cudaStream_t st);
-cudaError_t launch_pack_bender_t(const BenderSrc& src, void* packed_t, cudaStream_t st);
 
 }  // namespace nrn
