@@ -449,21 +449,24 @@ cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, float* ner
   if (p.compact) { first = 10; last = 12; p.stash_tile_bytes = kTanTileBytes; p.gstash_tile_bytes = kAdjTileBytes; }
   else { p.stash_tile_bytes = kStashTileBytes; p.gstash_tile_bytes = kGradTileBytes; }
   p.n_jobs = last - first;
-  long long total = 0;
-  for (int j = first; j < last; ++j) total += kJobChunks[j];
+  // Every CTA streams at the same bytes/clk (the kernel is HBM-bound), so the launch ends when the CTA with the most
+  // bytes ends: start with one CTA per job and hand each further CTA to the job whose CTAs currently carry the most
+  // (chunks per tile x tiles per CTA).
   int used = 0;
-  for (int j = first; j < last; ++j) {
-    int s = static_cast<int>((static_cast<long long>(num_sms) * kJobChunks[j]) / total);
-    if (s < 1) s = 1;
-    if (s > p.n_tiles) s = p.n_tiles > 0 ? p.n_tiles : 1;
-    p.job_ids[j - first] = j;
-    p.splits[j - first] = s;
-    used += s;
-  }
-  // hand the remainder to the biggest jobs, round robin
-  for (int guard = 0; used < num_sms && p.n_tiles > 0 && guard < 4 * num_sms; ++guard) {
-    const int j = p.compact ? guard % p.n_jobs : 1 + guard % 7;
-    if (p.splits[j] < p.n_tiles) { ++p.splits[j]; ++used; }
+  for (int j = first; j < last; ++j) { p.job_ids[j - first] = j; p.splits[j - first] = 1; ++used; }
+  const int tiles = p.n_tiles > 0 ? p.n_tiles : 1;
+  while (used < num_sms) {
+    int best = -1;
+    long long best_load = -1;
+    for (int j = first; j < last; ++j) {
+      const int sp = p.splits[j - first];
+      if (sp >= tiles) continue;   // a CTA needs at least one tile
+      const long long load = static_cast<long long>(kJobChunks[j]) * ((tiles + sp - 1) / sp);
+      if (load > best_load) { best_load = load; best = j; }
+    }
+    if (best < 0) break;
+    ++p.splits[best - first];
+    ++used;
   }
   if (p.n_tiles > 0) {
     const size_t smem = kWgStages * kStageBytes + sizeof(Shared) + 64;
