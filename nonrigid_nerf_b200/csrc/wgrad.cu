@@ -111,6 +111,21 @@ struct Waiter {
   }
 };
 
+// Sum over the warp's 32 lanes of v[j] for each j; lane L returns the total of column L.
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // which (job, split) does this CTA own?  job_ids[] / splits[] come from the host (WgradParams)
 __device__ __forceinline__ bool locate(const WgradParams& p, int cta, int& job, int& split, int& nsplit) {
   int base = 0;
@@ -210,45 +225,45 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     }
   } else {
     // ===================== bias column sums (8 warps), then accumulator drain =====================
-    const int t = threadIdx.x - 64;           // 0..255
-    const int c = t >> 3, g = t & 7;          // chunk, group of 16 points
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // db[feature] = sum over points of dY: warp w owns chunks 4w .. 4w+3 of the A block; lane l reads rows l, l+32,
+    // l+64, l+96 of each chunk (consecutive lanes = consecutive 16-byte rows: conflict-free, unlike a per-thread
+    // row-group walk, which put all 32 lanes on the same four banks), keeps 4 x 8 partial sums and a warp
+    // transpose-reduce leaves the total of (chunk 4w + L/8, feature L%8) in lane L.
+    const int bw = warp - 2;                  // 0..7
+    float acc = 0.f;
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < n_stages_total; ++it) {
       W.wait(&sh->full[stage], phase, 301);
-      if (jb.bias && (it & 1) == 0) {   // warp-uniform; an A stage.  Lanes whose chunk lies beyond the block contribute zeros
-        const bool live = c < jb.a_chunks;
-        const uint8_t* src = smem + stage * kStageBytes + c * kChunkBytes + g * 16 * 16;
-        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (live) {
+      if (jb.bias && (it & 1) == 0) {   // warp-uniform; an A stage
+        float s[32];
 #pragma unroll
-          for (int r = 0; r < 16; ++r) {
-            const uint4 w = *reinterpret_cast<const uint4*>(src + r * 16);
-            const __half2* h = reinterpret_cast<const __half2*>(&w);
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = bw * 4 + cc;
+          const uint8_t* src = smem + stage * kStageBytes + c * kChunkBytes + lane * 16;
+          float t8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (c < jb.a_chunks) {        // chunks beyond the block hold stale data
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = __half22float2(h[q]);
-              s[2 * q] += f.x; s[2 * q + 1] += f.y;
+            for (int r = 0; r < 4; ++r) {
+              const uint4 w = *reinterpret_cast<const uint4*>(src + r * 512);
+              const __half2* h = reinterpret_cast<const __half2*>(&w);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 f = __half22float2(h[q]);
+                t8[2 * q] += f.x; t8[2 * q + 1] += f.y;
+              }
             }
           }
-        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          s[q] += __shfl_xor_sync(0xffffffffu, s[q], 1);
-          s[q] += __shfl_xor_sync(0xffffffffu, s[q], 2);
-          s[q] += __shfl_xor_sync(0xffffffffu, s[q], 4);
-          acc[q] += s[q];
+          for (int q = 0; q < 8; ++q) s[cc * 8 + q] = t8[q];
         }
+        acc += warp_transpose_reduce(s, lane);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->empty[stage]);
       if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
     }
     float* part = p.scratch + static_cast<size_t>(blockIdx.x) * kWgScratchFloats;
-    if (have && jb.bias && g == 0 && c < jb.a_chunks) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) part[65536 + c * 8 + q] = acc[q];
-    }
+    if (have && jb.bias && (bw * 4 + (lane >> 3)) < jb.a_chunks) part[65536 + bw * 32 + lane] = acc;
     // drain: warps 2..5 own TMEM lane quarters (warp % 4)
     W.wait(&sh->done, 0, 302);
     tc_fence_after_sync();
