@@ -264,21 +264,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const WgradParams 
     }
     float* part = p.scratch + static_cast<size_t>(blockIdx.x) * kWgScratchFloats;
     if (have && jb.bias && (bw * 4 + (lane >> 3)) < jb.a_chunks) part[65536 + bw * 32 + lane] = acc;
-    // drain: warps 2..5 own TMEM lane quarters (warp % 4)
+    // drain the accumulators into this CTA's scratch partial once the last MMA has retired
     W.wait(&sh->done, 0, 302);
     tc_fence_after_sync();
 #ifdef NRN_TRACE
     if (threadIdx.x == 64) { g_wg_prof[blockIdx.x * 4 + 0] = job_id; g_wg_prof[blockIdx.x * 4 + 1] = t_end - t_begin; g_wg_prof[blockIdx.x * 4 + 2] = clock64() - prof_t0; }
 #endif
-    if (have && warp >= 2 && warp < 6) {
-      const int q4 = warp & 3;
+    if (have) {
+      // all 8 warps drain: warp % 4 selects the TMEM lane quarter, (warp - 2) / 4 the half of the 16-column blocks
+      const int q4 = warp & 3, hsel = (warp - 2) >> 2;
       const int m = q4 * 32 + lane;
       for (int s = 0; s < jb.n_sub; ++s) {
         const Sub sb = jb.sub[s];
         const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(q4) * 32u) << 16) + sb.tmem_col;
         // scratch layout: NeRF jobs [(half*128 + m)][256]; bender jobs [sub][m][128]
         float* dst_row = job_id <= 9 ? part + (s * 128 + m) * 256 : part + s * 16384 + m * 128;
-        for (int c0 = 0; c0 < sb.n; c0 += 16) {
+        const int nblk = sb.n / 16, nfirst = (nblk + 1) / 2;
+        const int b0 = hsel ? nfirst : 0, b1 = hsel ? nblk : nfirst;
+        for (int blk = b0; blk < b1; ++blk) {
+          const int c0 = blk * 16;
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
@@ -458,8 +462,10 @@ __global__ void wgrad_reduce_kernel(const WgradParams p, float* __restrict__ ner
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, float* nerf_grad, int nerf_n, float* bend_grad,
                          int bend_n, int out_ch, cudaStream_t st) {
-  // chunks (1 KB per 64-row stage) moved per stage by every job -> proportional split of the CTAs
-  static const int kJobChunks[12] = {2 + 32, 64, 64, 64, 64, 64, 64, 64, 32 + 8, 32 + 8, 20 + 28, 24 + 18};
+  // relative cost of one tile of every job = 2 KB chunks it moves; the head job (a 4 KB gradient block alternating
+  // with a 64 KB activation block keeps fewer bytes in flight) and the three-MMA bender job stream a little slower
+  // per byte (scripts/trace_wgrad.py), hence their surcharge
+  static const int kJobChunks[12] = {46, 64, 64, 64, 64, 64, 64, 64, 32 + 8, 32 + 8, 54, 24 + 18};
   int first = 0, last = has_bender ? 12 : 10;
   if (p.compact) { first = 10; last = 12; p.stash_tile_bytes = kTanTileBytes; p.gstash_tile_bytes = kAdjTileBytes; }
   else { p.stash_tile_bytes = kStashTileBytes; p.gstash_tile_bytes = kGradTileBytes; }
