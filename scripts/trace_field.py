@@ -8,6 +8,8 @@ import sys
 
 import torch
 
+os.environ.setdefault("NRN_PAIR", "1")   # the instrumented kernel is the CTA-pair forward; read once when the library loads
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle.nrnerf_oracle as O  # noqa: E402  (developer script, not a product path)
 from tests import helpers  # noqa: E402
