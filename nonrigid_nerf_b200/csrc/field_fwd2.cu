@@ -9,7 +9,11 @@
 //   * the single-CTA kernel was bound by the per-slot dependency chain
 //       MMA block (ring-latency bound: a 2 x 32 KB ring cannot cover the ~0.8 us slab reload)
 //       -> epilogue (one warpgroup, ~1.7 us per 128 x 256 tile) -> handshake -> next MMA block.
-// This version shortens every link of that chain:
+// This version (opt-in, NRN_PAIR=1; bit-identical output, tests/test_field_forward_gpu.py) attacks every link of that
+// chain.  Measured outcome on B200: 8.4 ms vs 8.0 ms of field_fwd.cu for 65,536 x 128 points without bender, 9.9 vs
+// 9.8 ms with, 0.394 vs 0.400 ms per training step -- a wash, because with a ring of exactly one layer slot 0's next
+// block waits for the reload that slot 1's use of the stage releases.  Kept as the starting
+// point for the deeper-ring version and as the repo's reference for the cluster / cta_group::2 protocol:
 //   * CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): a CTA holds only its N/2 rows of every weight
 //     slab, so the 64 KB ring holds a whole layer.  A slab is loaded ONCE per tile group, used by slot 0 and by
 //     slot 1, and recycled when both have consumed it: no ring-latency stalls, half the weight traffic.
