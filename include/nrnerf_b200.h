@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define NRN_ABI_VERSION 1
+#define NRN_ABI_VERSION 2
 
 #define NRN_OK 0
 #define NRN_E_INVALID (-1)   /* bad argument / unsupported configuration */
@@ -147,6 +147,12 @@ typedef struct NrnFieldBwdArgs {
   float* bender_grad;             /* out, nrn_bender_grad_floats() floats, overwritten (or NULL) */
   float* d_latents;               /* out [n_rays][32], overwritten (or NULL without bender) */
   void* stream;
+  /* Gradients written where PyTorch keeps them (SURVEY.md 8b "gradient buffers that alias param.grad"):
+   * nerf_grad_head, if not NULL, receives the output_linear part (Wout bout) instead of the tail of nerf_grad -- in
+   * module.parameters() order the dead views_linears sit between pts_linears and output_linear; accumulate_* != 0
+   * adds to the destination instead of overwriting it (what autograd's AccumulateGrad would do). */
+  float* nerf_grad_head;
+  int32_t accumulate_nerf, accumulate_bender;
 } NrnFieldBwdArgs;
 int nrn_field_backward(const NrnFieldBwdArgs* args);
 
@@ -178,6 +184,7 @@ typedef struct NrnDivArgs {
   float* d_rigidity_mask;          /* out [P]    gradient w.r.t. the coarse rigidity mask */
   float* bender_grad;              /* out, nrn_bender_grad_floats(): weight gradients of the tangent chain */
   void* stream;
+  int32_t accumulate_bender;       /* != 0: add to bender_grad instead of overwriting it */
 } NrnDivArgs;
 int nrn_divergence_forward(const NrnDivArgs* args);
 int nrn_divergence_backward(const NrnDivArgs* args);
@@ -200,6 +207,9 @@ typedef struct NrnRayLossArgs {
   float* u_unmasked_offsets;       /* out [n][S][3] */
   float* u_rigidity_mask;          /* out [n][S] */
   void* stream;
+  const float* lam_offsets_scale;  /* NULL, or device scalar multiplied into lam_offsets at run time: the regulariser
+                                      schedule (1/100)^(1 - global_step / N_iters) of train.py:229 as a device value, so
+                                      that a captured CUDA graph follows the schedule */
 } NrnRayLossArgs;
 int nrn_ray_loss(const NrnRayLossArgs* args);
 /* out[i] = g[i / per_row] * unit[i]  (backward of nrn_ray_loss) */
@@ -226,6 +236,32 @@ typedef struct NrnAdamArgs {
   void* stream;
 } NrnAdamArgs;
 int nrn_adam_step(const NrnAdamArgs* args);
+
+/* ---- multi-GPU: gradient all-reduce fused into the optimizer step over NVLink peer memory.  Replaces the gradient
+ * reduction torch.nn.DataParallel performs on GPU 0 (train.py:290-297; backward of the scatter at :1566-1577) plus the
+ * optimizer.step() at :1608, for one process per GPU on one node.  Every rank allocates a window
+ *   [ 1024 B flags | 2 x slot_floats floats (double-buffered row slots) | arena_floats floats (gradient arena) ]
+ * with nrn_peer_alloc, publishes its 64-byte CUDA IPC handle to the other ranks (any side channel: the host side uses
+ * torch.distributed.all_gather_object), maps theirs with nrn_peer_open, and points every parameter's .grad into its own
+ * window's arena.  nrn_peer_reduce_adam then sums the ranks' arenas in rank order while reading them over NVLink and applies
+ * Adam (same arithmetic as nrn_adam_step; grad_ptrs is ignored, gradients come from the arenas at the blocks' flat
+ * offsets); afterwards the arena holds the reduced gradient.  nrn_peer_gather_rows all-gathers n_per_rank floats per rank
+ * (the per-ray losses the caller logs) through the slots.  All launches are plain kernels on `stream` (CUDA-graph
+ * capturable); a peer that never arrives becomes device error 901/902/903 (nrn_device_error), not a hang. */
+size_t nrn_peer_window_bytes(int64_t arena_floats, int64_t slot_floats);
+int nrn_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_64bytes);
+int nrn_peer_open(const void* ipc_handle_64bytes, void** dev_ptr);
+int nrn_peer_close(void* dev_ptr);
+int nrn_peer_free(void* dev_ptr);
+typedef struct NrnPeerCtx {
+  void* window[8];          /* all ranks' windows as mapped into this process; window[rank] = own allocation */
+  int32_t world, rank;
+  int64_t arena_floats, slot_floats;
+  void* state;              /* device, 16 bytes, zero-initialised once: 3 epoch counters + block counter */
+  float* reduced;           /* device workspace, arena_floats floats */
+} NrnPeerCtx;
+int nrn_peer_reduce_adam(const NrnPeerCtx* ctx, const NrnAdamArgs* adam);
+int nrn_peer_gather_rows(const NrnPeerCtx* ctx, const float* local, int n_per_rank, float* out, void* stream);
 
 /* ---- optional per-kernel timing (measurement aid for bench.py) ---------------------------------
  * While enabled, every launch of the kernel kinds below is bracketed by CUDA events recorded on the

@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnrnerf_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _f32p = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -44,6 +44,7 @@ class NrnFieldBwdArgs(C.Structure):
         ("use_scaling", C.c_int32), ("scaling", C.c_float),
         ("nerf_grad", _vp), ("bender_grad", _vp), ("d_latents", _vp),
         ("stream", _vp),
+        ("nerf_grad_head", _vp), ("accumulate_nerf", C.c_int32), ("accumulate_bender", C.c_int32),
     ]
 
 
@@ -57,6 +58,7 @@ class NrnDivArgs(C.Structure):
         ("G", _vp), ("g_ray", _vp), ("G_workspace", _vp), ("adjoint_stash", _vp), ("wgrad_scratch", _vp), ("d_unmasked_offsets", _vp),
         ("d_rigidity_mask", _vp), ("bender_grad", _vp),
         ("stream", _vp),
+        ("accumulate_bender", C.c_int32),
     ]
 
 
@@ -67,6 +69,7 @@ class NrnRayLossArgs(C.Structure):
         ("lam_offsets", C.c_float), ("lam_rigidity", C.c_float),
         ("loss", _vp), ("u_rgb", _vp), ("u_rgb0", _vp), ("u_unmasked_offsets", _vp), ("u_rigidity_mask", _vp),
         ("stream", _vp),
+        ("lam_offsets_scale", _vp),
     ]
 
 
@@ -74,6 +77,13 @@ class NrnAdamArgs(C.Structure):
     _fields_ = [
         ("params", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("grad_ptrs", _vp), ("blocks", _vp), ("n_tensors", C.c_int32), ("n_blocks", C.c_int32),
         ("lr", _vp), ("step", _vp), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("stream", _vp),
+    ]
+
+
+class NrnPeerCtx(C.Structure):
+    _fields_ = [
+        ("window", _vp * 8), ("world", C.c_int32), ("rank", C.c_int32), ("arena_floats", C.c_int64), ("slot_floats", C.c_int64),
+        ("state", _vp), ("reduced", _vp),
     ]
 
 
@@ -123,6 +133,13 @@ SYMBOLS = {
     "nrn_ray_loss": (C.c_int, [C.POINTER(NrnRayLossArgs)]),
     "nrn_scale_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
     "nrn_adam_step": (C.c_int, [C.POINTER(NrnAdamArgs)]),
+    "nrn_peer_window_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "nrn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), C.c_char_p]),
+    "nrn_peer_open": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
+    "nrn_peer_close": (C.c_int, [_vp]),
+    "nrn_peer_free": (C.c_int, [_vp]),
+    "nrn_peer_reduce_adam": (C.c_int, [C.POINTER(NrnPeerCtx), C.POINTER(NrnAdamArgs)]),
+    "nrn_peer_gather_rows": (C.c_int, [C.POINTER(NrnPeerCtx), _vp, C.c_int, _vp, _vp]),
     "nrn_timing_enable": (C.c_int, [C.c_int]),
     "nrn_timing_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]),
 }

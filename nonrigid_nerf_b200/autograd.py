@@ -66,10 +66,13 @@ class _ParamGroupFn(torch.autograd.Function):
     def forward(ctx, *params):
         ctx.shapes = [p.shape for p in params]
         ctx.needs = [p.requires_grad for p in params]
+        ctx.set_materialize_grads(False)
         return params[0].new_empty(1).expand(sum(p.numel() for p in params))
 
     @staticmethod
     def backward(ctx, flat):
+        if flat is None:     # every user of the group wrote its gradient straight into the parameters' .grad arena
+            return (None,) * len(ctx.shapes)
         out, o = [], 0
         for shp, need in zip(ctx.shapes, ctx.needs):
             n = 1
@@ -150,9 +153,22 @@ class _FieldTrainFn(torch.autograd.Function):
         scratch = torch.empty(lib.nrn_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
         a.grad_stash, a.wgrad_scratch = gstash.data_ptr(), scratch.data_ptr()
         a.nerf_packed = nerf_pack.data_ptr()
-        nerf_grad = torch.empty(lib.nrn_nerf_grad_floats(out_ch), dtype=torch.float32, device=dev)
-        a.nerf_grad = nerf_grad.data_ptr()
+        # Where the weight gradients go.  If the .grad tensors of this module's parameters lie back to back in one buffer
+        # (optim.Adam's arena) the WGRAD reduction ADDS into them in place and autograd gets nothing to accumulate;
+        # otherwise fresh flat buffers are handed to autograd as per-parameter views (torch.optim.Adam, or after the
+        # caller re-bound gradients -- the reference sets weights.grad = None between its two backward passes,
+        # train.py:1598-1604).
+        nerf_p = list(ctx.params[:ctx.n_nerf])
+        pts_dst = _arena_destination(nerf_p[:-2]) if all(p.requires_grad for p in nerf_p) else None
+        head_dst = _arena_destination(nerf_p[-2:]) if pts_dst is not None else None
+        nerf_grad = None
+        if head_dst is not None:
+            a.nerf_grad, a.nerf_grad_head, a.accumulate_nerf = pts_dst, head_dst, 1
+        else:
+            nerf_grad = torch.empty(lib.nrn_nerf_grad_floats(out_ch), dtype=torch.float32, device=dev)
+            a.nerf_grad = nerf_grad.data_ptr()
         bend_grad = d_lat = None
+        bend_in_place = False
         keep = [d_raw]
         if bender is not None:
             un, rig = ctx.saved_tensors
@@ -170,18 +186,82 @@ class _FieldTrainFn(torch.autograd.Function):
                 a.use_cutoff, a.rigidity_cutoff = 1, float(cutoff)
             if scaling is not None:
                 a.use_scaling, a.scaling = 1, float(scaling)
-            bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
+            bend_dst = _bender_arena(bender)
+            if bend_dst is not None:
+                a.bender_grad, a.accumulate_bender, bend_in_place = bend_dst, 1, True
+            else:
+                bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
+                a.bender_grad = bend_grad.data_ptr()
             d_lat = torch.empty(n, ops.LATENT, dtype=torch.float32, device=dev)
-            a.bender_grad, a.d_latents = bend_grad.data_ptr(), d_lat.data_ptr()
+            a.d_latents = d_lat.data_ptr()
         a.stream = torch.cuda.current_stream().cuda_stream
         with torch.cuda.device(dev):
             _lib.check(lib.nrn_field_backward(C.byref(a)), "field_backward")
-        ctx.stash = None
-        nerf_p = ctx.params[:ctx.n_nerf]
-        grads = [g if p.requires_grad else None for g, p in zip(_split_flat(nerf_grad, nerf_p), nerf_p)]
+        # the stash lives as long as the autograd node: backward(retain_graph=True) followed by a second backward()
+        # over the same graph (test-latent pass of the reference loop, train.py:1595-1606) reads it again
+        if nerf_grad is None:
+            grads = [None] * len(nerf_p)
+        else:
+            grads = [g if p.requires_grad else None for g, p in zip(_split_flat(nerf_grad, nerf_p), nerf_p)]
         if bender is not None:
-            grads.append(bend_grad)     # flat, for the bender's group token
+            grads.append(None if bend_in_place else bend_grad)     # flat, for the bender's group token
         return (None, None, None, d_lat, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------------
+# gradient arena look-ups (optim.Adam seats every .grad as a view of one flat buffer)
+# ---------------------------------------------------------------------------------------------
+def _arena_destination(params):
+    from .optim import arena_destination
+    return arena_destination(list(params))
+
+
+def _bender_arena(bender):
+    _, bend_p = _flat_params_bender(bender)
+    if not all(p.requires_grad for p in bend_p):
+        return None
+    return _arena_destination(bend_p)
+
+
+class _LatentGatherFn(torch.autograd.Function):
+    """latents[timestep[i]] for every ray i (train.py:173-189: stack the per-frame latents, index by the ray's time step).
+    The per-frame latents are views of the optimizer's flat buffer, so the table is read in place; the backward adds the
+    per-ray gradients [N, Z] into the latents' .grad arena with one index_add_ (fallback: per-latent gradient views)."""
+
+    @staticmethod
+    def forward(ctx, timestep, *latents):
+        z = latents[0].numel()
+        base, contiguous = latents[0].data_ptr(), True
+        for i, l in enumerate(latents):
+            if l.data_ptr() != base + 4 * z * i or l.dtype != torch.float32 or not l.is_contiguous():
+                contiguous = False
+                break
+        if contiguous and latents[0].untyped_storage().nbytes() >= latents[0].storage_offset() * 4 + 4 * z * len(latents):
+            table = latents[0].detach().as_strided((len(latents), z), (z, 1))
+        else:
+            table = torch.stack([l.detach() for l in latents], 0)
+        ctx.save_for_backward(timestep)
+        ctx.latents = latents
+        ctx.z = z
+        return torch.index_select(table, 0, timestep)
+
+    @staticmethod
+    def backward(ctx, d_sel):
+        (timestep,) = ctx.saved_tensors
+        latents, z = ctx.latents, ctx.z
+        t = len(latents)
+        dst = _arena_destination(latents) if all(l.requires_grad for l in latents) else None
+        if dst is not None:
+            g0 = latents[0].grad
+            g0.as_strided((t, z), (z, 1)).index_add_(0, timestep, d_sel.contiguous().float())
+            return (None,) * (t + 1)
+        g = torch.zeros(t, z, dtype=torch.float32, device=d_sel.device).index_add_(0, timestep, d_sel.float())
+        return (None, *[g[i] if l.requires_grad else None for i, l in enumerate(latents)])
+
+
+def gather_latents(latents, timestep: torch.Tensor) -> torch.Tensor:
+    """[N, Z] per-ray latents from the list of per-frame leaf tensors and the rays' time-step ids."""
+    return _LatentGatherFn.apply(timestep, *latents)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -198,6 +278,18 @@ def _register_stash(unmasked: torch.Tensor, stash: torch.Tensor) -> None:
 
 
 def lookup_stash(unmasked: torch.Tensor) -> Optional[torch.Tensor]:
+    """The activation stash of the coarse pass that produced `unmasked`: found by walking the tensor's autograd history
+    (through the reshapes of render()) to the _FieldTrainFn node, which owns the stash; the address table is only the
+    fallback for detached tensors."""
+    fn = unmasked.grad_fn
+    for _ in range(8):
+        if fn is None:
+            break
+        stash = getattr(fn, "stash", None)
+        if isinstance(stash, torch.Tensor):
+            return stash
+        nxt = [f for f, _ in fn.next_functions if f is not None]
+        fn = nxt[0] if len(nxt) == 1 else None
     ref = _STASH_BY_PTR.get(unmasked.data_ptr())
     return ref() if ref is not None else None
 
@@ -261,13 +353,18 @@ class _DivergenceFn(torch.autograd.Function):
         scratch = torch.empty(lib.nrn_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
         d_un = torch.empty(n * s, 3, dtype=torch.float32, device=dev)
         d_rg = torch.empty(n * s, dtype=torch.float32, device=dev)
-        bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
+        bend_dst = _bender_arena(bender)
+        bend_grad = None
+        if bend_dst is not None:
+            a.bender_grad, a.accumulate_bender = bend_dst, 1
+        else:
+            bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
+            a.bender_grad = bend_grad.data_ptr()
         a.adjoint_stash, a.wgrad_scratch = adj.data_ptr(), scratch.data_ptr()
-        a.d_unmasked_offsets, a.d_rigidity_mask, a.bender_grad = d_un.data_ptr(), d_rg.data_ptr(), bend_grad.data_ptr()
+        a.d_unmasked_offsets, a.d_rigidity_mask = d_un.data_ptr(), d_rg.data_ptr()
         a.stream = torch.cuda.current_stream().cuda_stream
         with torch.cuda.device(dev):
             _lib.check(lib.nrn_divergence_backward(C.byref(a)), "divergence_backward")
-        ctx.keep = None
         return (d_un.view(ctx.in_shapes[0]), d_rg.view(ctx.in_shapes[1]), None, None, None, None, bend_grad, None)
 
 
@@ -307,7 +404,7 @@ class _RayLossFn(torch.autograd.Function):
     """Per-ray loss of training_wrapper_class.forward (train.py:208-242) in one kernel (csrc/loss.cu)."""
 
     @staticmethod
-    def forward(ctx, rgb, rgb0, target, weights, unmasked, rigidity, lam_o, lam_r):
+    def forward(ctx, rgb, rgb0, target, weights, unmasked, rigidity, lam_o, lam_r, lam_o_scale=None):
         n = rgb.shape[0]
         dev = rgb.device
         lib = _lib.load()
@@ -332,6 +429,9 @@ class _RayLossFn(torch.autograd.Function):
             a.u_unmasked_offsets, a.u_rigidity_mask = u_off.data_ptr(), u_rig.data_ptr()
         a.n_rays, a.n_samples = n, s
         a.lam_offsets, a.lam_rigidity = float(lam_o), float(lam_r)
+        if lam_o_scale is not None:
+            keep.append(lam_o_scale.detach().float().contiguous())
+            a.lam_offsets_scale = keep[-1].data_ptr()
         loss = torch.empty(n, dtype=torch.float32, device=dev)
         a.loss = loss.data_ptr()
         a.stream = torch.cuda.current_stream().cuda_stream
@@ -355,12 +455,14 @@ class _RayLossFn(torch.autograd.Function):
                                               u.numel() // g.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "scale_rows")
             outs.append(o)
         d_rgb, d_rgb0, d_off, d_rig = outs
-        return d_rgb, d_rgb0, None, None, d_off, d_rig, None, None
+        return d_rgb, d_rgb0, None, None, d_off, d_rig, None, None, None
 
 
-def ray_loss(rgb, rgb0, target, weights=None, unmasked=None, rigidity=None, lam_offsets=0.0, lam_rigidity=0.0):
-    """loss[N] = img2mse(rgb) + img2mse(rgb0) + lam_offsets * (offsets + lam_rigidity * rigidity regulariser)."""
-    return _RayLossFn.apply(rgb, rgb0, target, weights, unmasked, rigidity, lam_offsets, lam_rigidity)
+def ray_loss(rgb, rgb0, target, weights=None, unmasked=None, rigidity=None, lam_offsets=0.0, lam_rigidity=0.0,
+             lam_offsets_scale: Optional[torch.Tensor] = None):
+    """loss[N] = img2mse(rgb) + img2mse(rgb0) + lam_offsets * (offsets + lam_rigidity * rigidity regulariser).
+    `lam_offsets_scale` (0-dim CUDA tensor) is multiplied into lam_offsets on the device (CUDA-graph-safe schedule)."""
+    return _RayLossFn.apply(rgb, rgb0, target, weights, unmasked, rigidity, lam_offsets, lam_rigidity, lam_offsets_scale)
 
 
 class _CompositeFn(torch.autograd.Function):

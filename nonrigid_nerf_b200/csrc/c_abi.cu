@@ -12,6 +12,7 @@
 #include "div.cuh"
 #include "loss.cuh"
 #include "adam.cuh"
+#include "peer.cuh"
 
 namespace nrn {
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
@@ -278,9 +279,14 @@ int nrn_field_backward(const NrnFieldBwdArgs* a) {
     e = cudaMemsetAsync(a->d_latents, 0, sizeof(float) * static_cast<size_t>(a->n_rays) * nrn::kLatent, st);
     if (e != cudaSuccess) return cuda_fail(e, "memset d_latents");
   }
-  if (a->n_rays == 0) {
-    e = cudaMemsetAsync(a->nerf_grad, 0, sizeof(float) * nerf_n, st);
-    if (e == cudaSuccess && bend) e = cudaMemsetAsync(a->bender_grad, 0, sizeof(float) * bend_n, st);
+  if (a->n_rays == 0) {   // an empty shard contributes zero gradients
+    e = cudaSuccess;
+    if (!a->accumulate_nerf) {
+      const int head_n = a->nerf_grad_head ? a->out_ch * 257 : 0;
+      e = cudaMemsetAsync(a->nerf_grad, 0, sizeof(float) * (nerf_n - head_n), st);
+      if (e == cudaSuccess && head_n) e = cudaMemsetAsync(a->nerf_grad_head, 0, sizeof(float) * head_n, st);
+    }
+    if (e == cudaSuccess && bend && !a->accumulate_bender) e = cudaMemsetAsync(a->bender_grad, 0, sizeof(float) * bend_n, st);
     return e == cudaSuccess ? NRN_OK : cuda_fail(e, "memset grads");
   }
   if (!a->d_raw || !a->stash || !a->grad_stash || !a->wgrad_scratch) return fail(NRN_E_INVALID, "nrn_field_backward: null argument");
@@ -298,12 +304,17 @@ int nrn_field_backward(const NrnFieldBwdArgs* a) {
   p.cutoff = a->rigidity_cutoff; p.use_cutoff = a->use_cutoff; p.scaling = a->scaling; p.use_scaling = a->use_scaling;
   p.d_latents = a->d_latents; p.err = ds->err_word;
   e = nrn::launch_absmax(a->d_raw, p.P * a->out_ch, amax, st);
+  // the regularisers' upstream gradients share the fp16 loss scale: they take part in the maximum, otherwise a large
+  // offsets_loss_weight saturates them (or, with a vanishing data term, lets them underflow)
+  if (e == cudaSuccess && bend && p.d_unmasked_up) e = nrn::launch_absmax(p.d_unmasked_up, p.P * 3, amax, st, true);
+  if (e == cudaSuccess && bend && p.d_rigid_up) e = nrn::launch_absmax(p.d_rigid_up, p.P, amax, st, true);
   if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
   { ScopedTimer tm(1, st); e = nrn::launch_field_bwd(p, bend, ds->num_sms, st); }
   if (e != cudaSuccess) return cuda_fail(e, "field_bwd_kernel");
   nrn::WgradParams w{};
   w.stash = p.stash; w.gstash = p.gstash; w.scratch = a->wgrad_scratch; w.amax = amax; w.n_tiles = p.n_tiles; w.err = ds->err_word;
-  { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, bend, ds->num_sms, a->nerf_grad, nerf_n, a->bender_grad, bend_n, a->out_ch, st); }
+  const nrn::WgradDst dst{a->nerf_grad, a->nerf_grad_head, a->bender_grad, nerf_n, bend_n, a->accumulate_nerf, a->accumulate_bender};
+  { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, bend, ds->num_sms, dst, a->out_ch, st); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "wgrad_kernel");
 }
 
@@ -364,7 +375,8 @@ int nrn_divergence_backward(const NrnDivArgs* a) {
   nrn::WgradParams w{};
   w.stash = p.tan; w.gstash = p.adj; w.scratch = a->wgrad_scratch; w.amax = amax; w.compact = 1;
   w.n_tiles = static_cast<int>((p.P + nrn::kTileM - 1) / nrn::kTileM); w.err = ds->err_word;
-  { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, true, ds->num_sms, nullptr, 0, a->bender_grad, nrn_bender_grad_floats(), 5, st); }
+  const nrn::WgradDst dst{nullptr, nullptr, a->bender_grad, 0, nrn_bender_grad_floats(), 0, a->accumulate_bender};
+  { ScopedTimer tm(2, st); e = nrn::launch_wgrad(w, true, ds->num_sms, dst, 5, st); }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "wgrad_kernel (divergence)");
 }
 
@@ -378,7 +390,7 @@ int nrn_ray_loss(const NrnRayLossArgs* a) {
   nrn::RayLossParams p{};
   p.n = a->n_rays; p.S = a->n_samples;
   p.rgb = a->rgb; p.rgb0 = a->rgb0; p.target = a->target; p.w = a->weights; p.off = a->unmasked_offsets; p.rig = a->rigidity_mask;
-  p.lam_o = a->lam_offsets; p.lam_r = a->lam_rigidity;
+  p.lam_o = a->lam_offsets; p.lam_r = a->lam_rigidity; p.lam_o_scale = a->lam_offsets_scale;
   p.loss = a->loss; p.u_rgb = a->u_rgb; p.u_rgb0 = a->u_rgb0; p.u_off = a->u_unmasked_offsets; p.u_rig = a->u_rigidity_mask;
   cudaError_t e = nrn::launch_ray_loss(p, static_cast<cudaStream_t>(a->stream));
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_loss_kernel");
@@ -392,20 +404,119 @@ int nrn_scale_rows(const float* g, const float* unit, float* out, int64_t n, int
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_loss_scale_kernel");
 }
 
+static int fill_adam(const NrnAdamArgs* a, nrn::AdamParams& p, const char* who, bool need_grads);
 int nrn_adam_step(const NrnAdamArgs* a) {
-  if (!a) return fail(NRN_E_INVALID, "nrn_adam_step: null args");
-  if (a->n_blocks < 0 || a->n_tensors < 0) return fail(NRN_E_INVALID, "nrn_adam_step: n_tensors = %d, n_blocks = %d", a->n_tensors, a->n_blocks);
-  if (!a->params || !a->exp_avg || !a->exp_avg_sq || !a->grad_ptrs || !a->blocks || !a->lr || !a->step)
-    return fail(NRN_E_INVALID, "nrn_adam_step: null buffer");
-  if (!(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->eps >= 0.f))
-    return fail(NRN_E_INVALID, "nrn_adam_step: betas / eps out of range");
   nrn::AdamParams p{};
+  const int rc = fill_adam(a, p, "nrn_adam_step", true);
+  if (rc) return rc;
+  const cudaError_t e = nrn::launch_adam(p, a->n_tensors, a->n_blocks, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "adam_kernel");
+}
+
+static int fill_adam(const NrnAdamArgs* a, nrn::AdamParams& p, const char* who, bool need_grads) {
+  if (!a) return fail(NRN_E_INVALID, "%s: null args", who);
+  if (a->n_blocks < 0 || a->n_tensors < 0) return fail(NRN_E_INVALID, "%s: n_tensors = %d, n_blocks = %d", who, a->n_tensors, a->n_blocks);
+  if (!a->params || !a->exp_avg || !a->exp_avg_sq || (need_grads && !a->grad_ptrs) || !a->blocks || !a->lr || !a->step)
+    return fail(NRN_E_INVALID, "%s: null buffer", who);
+  if (!(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f && a->eps >= 0.f))
+    return fail(NRN_E_INVALID, "%s: betas / eps out of range", who);
   p.params = static_cast<float*>(a->params); p.exp_avg = static_cast<float*>(a->exp_avg); p.exp_avg_sq = static_cast<float*>(a->exp_avg_sq);
   p.grads = static_cast<const float* const*>(a->grad_ptrs); p.blocks = static_cast<const nrn::AdamBlock*>(a->blocks);
   p.lr = static_cast<const float*>(a->lr); p.step = static_cast<long long*>(a->step);
   p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
-  const cudaError_t e = nrn::launch_adam(p, a->n_tensors, a->n_blocks, static_cast<cudaStream_t>(a->stream));
-  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "adam_kernel");
+  return NRN_OK;
+}
+
+size_t nrn_peer_window_bytes(int64_t arena_floats, int64_t slot_floats) {
+  if (arena_floats < 0 || slot_floats < 0) return 0;
+  const size_t slot_bytes = (static_cast<size_t>(slot_floats) * 4 + 255) / 256 * 256;
+  return nrn::kPeerFlagBytes + 2 * slot_bytes + (static_cast<size_t>(arena_floats) * 4 + 255) / 256 * 256;
+}
+
+int nrn_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle) {
+  if (!dev_ptr || !ipc_handle || bytes < nrn::kPeerFlagBytes) return fail(NRN_E_INVALID, "nrn_peer_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(peer window)");
+  e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(ipc_handle, &h, sizeof(h));
+  *dev_ptr = p;
+  return NRN_OK;
+}
+
+int nrn_peer_open(const void* ipc_handle, void** dev_ptr) {
+  if (!ipc_handle || !dev_ptr) return fail(NRN_E_INVALID, "nrn_peer_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (peer-to-peer access between the GPUs of this node is required)");
+  *dev_ptr = p;
+  return NRN_OK;
+}
+
+int nrn_peer_close(void* dev_ptr) {
+  if (!dev_ptr) return NRN_OK;
+  const cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "cudaIpcCloseMemHandle");
+}
+
+int nrn_peer_free(void* dev_ptr) {
+  if (!dev_ptr) return NRN_OK;
+  const cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "cudaFree(peer window)");
+}
+
+static int fill_peer(const NrnPeerCtx* c, nrn::PeerCtx& p, const char* who) {
+  if (!c) return fail(NRN_E_INVALID, "%s: null context", who);
+  if (c->world < 1 || c->world > nrn::kPeerMaxRanks || c->rank < 0 || c->rank >= c->world)
+    return fail(NRN_E_INVALID, "%s: world = %d, rank = %d (at most %d ranks of one node)", who, c->world, c->rank, nrn::kPeerMaxRanks);
+  if (!c->state || c->arena_floats < 0 || c->slot_floats < 0) return fail(NRN_E_INVALID, "%s: bad context", who);
+  for (int r = 0; r < c->world; ++r) {
+    if (!c->window[r]) return fail(NRN_E_INVALID, "%s: window of rank %d not mapped", who, r);
+    p.window[r] = static_cast<uint8_t*>(c->window[r]);
+  }
+  p.world = c->world; p.rank = c->rank;
+  p.slot_off = nrn::kPeerFlagBytes;
+  p.slot_bytes = (static_cast<size_t>(c->slot_floats) * 4 + 255) / 256 * 256;
+  p.arena_off = p.slot_off + 2 * p.slot_bytes;
+  return NRN_OK;
+}
+
+int nrn_peer_reduce_adam(const NrnPeerCtx* c, const NrnAdamArgs* a) {
+  nrn::PeerCtx pc{};
+  int rc = fill_peer(c, pc, "nrn_peer_reduce_adam");
+  if (rc) return rc;
+  nrn::AdamParams p{};
+  rc = fill_adam(a, p, "nrn_peer_reduce_adam", false);
+  if (rc) return rc;
+  if (!c->reduced) return fail(NRN_E_INVALID, "nrn_peer_reduce_adam: null workspace");
+  DeviceState* ds;
+  rc = device_state(&ds);
+  if (rc) return rc;
+  uint32_t* state = static_cast<uint32_t*>(c->state);
+  const cudaError_t e = nrn::launch_peer_reduce_adam(pc, p, a->n_tensors, a->n_blocks, c->arena_floats, state, c->reduced, state + 3,
+                                                     ds->err_word, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "peer_adam_kernel");
+}
+
+int nrn_peer_gather_rows(const NrnPeerCtx* c, const float* local, int n_per_rank, float* out, void* stream) {
+  nrn::PeerCtx pc{};
+  int rc = fill_peer(c, pc, "nrn_peer_gather_rows");
+  if (rc) return rc;
+  if (n_per_rank < 0 || n_per_rank > c->slot_floats) return fail(NRN_E_INVALID, "nrn_peer_gather_rows: %d floats per rank exceed the slot (%lld)", n_per_rank, (long long)c->slot_floats);
+  if (n_per_rank == 0) return NRN_OK;
+  if (!local || !out) return fail(NRN_E_INVALID, "nrn_peer_gather_rows: null argument");
+  DeviceState* ds;
+  rc = device_state(&ds);
+  if (rc) return rc;
+  const cudaError_t e = nrn::launch_peer_gather(pc, static_cast<uint32_t*>(c->state), local, n_per_rank, out, ds->err_word, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "peer_collect_kernel");
 }
 
 int nrn_timing_enable(int on) {

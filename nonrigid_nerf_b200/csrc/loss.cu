@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_loss_kernel(const Ray
     }
   }
   if (p.off) {
+    const float lam_o = p.lam_o_scale ? p.lam_o * __ldg(p.lam_o_scale) : p.lam_o;
     const float inv_s = 1.0f / static_cast<float>(p.S);
     float acc = 0.f;
     for (int i = lane; i < p.S; i += 32) {
@@ -55,12 +56,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_loss_kernel(const Ray
         f = 1.0f;                            // torch.pow(0, 0) = 1
       }
       acc += w * (f + p.lam_r * r);
-      const float c = p.lam_o * w * inv_s;
+      const float c = lam_o * w * inv_s;
       const float k = nrm > 0.f ? c * dn / nrm : 0.f;   // d||o||/do = o / ||o||, defined as 0 at 0
       p.u_off[pt * 3] = k * ox; p.u_off[pt * 3 + 1] = k * oy; p.u_off[pt * 3 + 2] = k * oz;
       p.u_rig[pt] = c * (dr + p.lam_r);
     }
-    loss += p.lam_o * acc * inv_s;
+    loss += lam_o * acc * inv_s;
   }
   loss = warp_sum(loss);
   if (lane == 0) p.loss[ray] = loss;

@@ -13,6 +13,7 @@ struct RayLossParams {
   const float* off;     // [n][S][3] coarse unmasked offsets or null (no offsets term)
   const float* rig;     // [n][S] coarse rigidity mask
   float lam_o, lam_r;
+  const float* lam_o_scale;   // device scalar multiplied into lam_o, or null
   float* loss;          // [n]
   float* u_rgb;         // [n][3]   gradients per unit upstream gradient
   float* u_rgb0;        // [n][3]

@@ -18,10 +18,12 @@ __global__ void absmax_kernel(const float* __restrict__ x, long long n, float* _
 }
 }  // namespace
 
-cudaError_t launch_absmax(const float* x, long long n, float* amax, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float), st);
-  if (e != cudaSuccess) return e;
-  if (n <= 0) return cudaSuccess;
+cudaError_t launch_absmax(const float* x, long long n, float* amax, cudaStream_t st, bool accumulate) {
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(amax, 0, sizeof(float), st);
+    if (e != cudaSuccess) return e;
+  }
+  if (n <= 0 || !x) return cudaSuccess;
   long long blocks = (n + 1023) / 1024;
   if (blocks > 1184) blocks = 1184;
   absmax_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, n, amax);

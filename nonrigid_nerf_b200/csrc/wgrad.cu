@@ -403,9 +403,9 @@ __device__ __forceinline__ Src bender_src(int idx, bool& ok) {
 
 }  // namespace
 
-__global__ void wgrad_reduce_kernel(const WgradParams p, float* __restrict__ nerf_grad, int nerf_n,
-                                    float* __restrict__ bend_grad, int bend_n, int out_ch) {
+__global__ void wgrad_reduce_kernel(const WgradParams p, const WgradDst dst, int out_ch) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nerf_n = dst.nerf_n, bend_n = dst.bend_n;
   if (idx >= nerf_n + bend_n) return;
   bool ok;
   const Src s = idx < nerf_n ? nerf_src(idx, out_ch, ok) : bender_src(idx - nerf_n, ok);
@@ -456,12 +456,21 @@ __global__ void wgrad_reduce_kernel(const WgradParams p, float* __restrict__ ner
     }
   }
   const float v = sum / scale;
-  if (idx < nerf_n) nerf_grad[idx] = v; else bend_grad[idx - nerf_n] = v;
+  float* out;
+  bool acc;
+  if (idx < nerf_n) {
+    const int n_pts = nerf_n - out_ch * 257;
+    out = (idx >= n_pts && dst.nerf_head) ? dst.nerf_head + (idx - n_pts) : dst.nerf + idx;
+    acc = dst.acc_nerf != 0;
+  } else {
+    out = dst.bend + (idx - nerf_n);
+    acc = dst.acc_bend != 0;
+  }
+  *out = acc ? *out + v : v;
 }
 
 // ------------------------------------------------------------------------------------------------
-cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, float* nerf_grad, int nerf_n, float* bend_grad,
-                         int bend_n, int out_ch, cudaStream_t st) {
+cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, const WgradDst& dst, int out_ch, cudaStream_t st) {
   // relative cost of one tile of every job = 2 KB chunks it moves; the head job (a 4 KB gradient block alternating
   // with a 64 KB activation block keeps fewer bytes in flight) and the three-MMA bender job stream a little slower
   // per byte (scripts/trace_wgrad.py), hence their surcharge
@@ -497,8 +506,8 @@ cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, float* ner
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  const int n = nerf_n + bend_n;
-  if (n > 0) wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, nerf_grad, nerf_n, bend_grad, bend_n, out_ch);
+  const int n = dst.nerf_n + dst.bend_n;
+  if (n > 0) wgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, dst, out_ch);
   return cudaGetLastError();
 }
 

@@ -22,9 +22,17 @@ struct WgradParams {
   int* err;
 };
 
-cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, float* nerf_grad, int nerf_n, float* bend_grad,
-                         int bend_n, int out_ch, cudaStream_t st);
+// Destination of the reduced gradients.  nerf: pts_linears part (nerf_n - out_ch * 257 floats) then, at `nerf_head` when
+// given (else directly behind), the output_linear part.  acc_* : add to the destination instead of overwriting it.
+struct WgradDst {
+  float* nerf;
+  float* nerf_head;
+  float* bend;
+  int nerf_n, bend_n;
+  int acc_nerf, acc_bend;
+};
+cudaError_t launch_wgrad(WgradParams p, bool has_bender, int num_sms, const WgradDst& dst, int out_ch, cudaStream_t st);
 // amax[0] = max |x[i]| over n floats (device scalar, overwritten)
-cudaError_t launch_absmax(const float* x, long long n, float* amax, cudaStream_t st);
+cudaError_t launch_absmax(const float* x, long long n, float* amax, cudaStream_t st, bool accumulate = false);
 
 }  // namespace nrn

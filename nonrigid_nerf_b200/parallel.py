@@ -150,18 +150,60 @@ def all_reduce_gradients(params: List[torch.Tensor]) -> None:
 
 
 _HOOK_INSTALLED = False
+_SHARDED_PARAM_IDS: set = set()   # id() of every tensor a ray-sharded training function differentiates
 UNIFORM_GRADS = False   # True: a gradient that is None on one rank is None on all (skips the presence flags + host sync)
 
 
+def _register_sharded_params(params) -> None:
+    for p in params:
+        _SHARDED_PARAM_IDS.add(id(p))
+
+
+def _owns_sharded_params(optimizer) -> bool:
+    """Only an optimizer that steps parameters of a ray-sharded training function takes part in the gradient
+    all-reduce.  Any other optimizer in the process (a CPU baseline, a user's second model) is left alone."""
+    for g in optimizer.param_groups:
+        for p in g["params"]:
+            if id(p) in _SHARDED_PARAM_IDS:
+                return True
+    return False
+
+
+class NcclArenaReducer:
+    """In-place SUM all-reduce over an optim.Adam gradient arena: ONE collective over ONE persistent buffer whose views
+    are the parameters' .grad tensors (no gather before, no scatter after)."""
+
+    fused_adam = False
+
+    def step(self, optimizer, adam_args) -> bool:
+        if _world() > 1:
+            dist.all_reduce(optimizer.gradient_arena(), op=dist.ReduceOp.SUM)
+        return False        # the optimizer launches its Adam kernel on the reduced arena
+
+
+def attach_optimizer(optimizer, reducer=None) -> None:
+    """Tell an nonrigid_nerf_b200.optim.Adam that its parameters are trained ray-sharded: its step() then reduces the
+    gradient arena across ranks itself.  Called automatically (with the NCCL reducer) from the optimizer hook the first
+    time such an optimizer steps; call it explicitly to install another reducer (peer.PeerArenaReducer)."""
+    if hasattr(optimizer, "gradient_arena"):
+        optimizer._reducer = reducer if reducer is not None else NcclArenaReducer()
+
+
 def _install_optimizer_hook() -> None:
-    """Global optimizer pre-step hook: all-reduce the gradients of everything the optimizer owns."""
+    """Optimizer pre-step hook (the reference builds its optimizer before it builds the parallel wrappers and never
+    hands it over, train.py:656-658 vs :1455-1461, so the hook cannot be attached to one instance): all-reduce the
+    gradients of an optimizer that owns the sharded parameters; every other optimizer passes through untouched."""
     global _HOOK_INSTALLED
     if _HOOK_INSTALLED:
         return
     from torch.optim.optimizer import register_optimizer_step_pre_hook
 
     def hook(optimizer, args, kwargs):
-        if _world() > 1:
+        if _world() == 1 or not _owns_sharded_params(optimizer):
+            return
+        if hasattr(optimizer, "gradient_arena") and getattr(optimizer, "_reducer", None) is None:
+            attach_optimizer(optimizer)
+        if not getattr(optimizer, "reduces_gradients_itself", False):
             all_reduce_gradients([p for g in optimizer.param_groups for p in g["params"]])
 
     register_optimizer_step_pre_hook(hook)
@@ -222,32 +264,43 @@ class training_wrapper_class(torch.nn.Module):
             self.fine_model.ray_bender = (self.ray_bender,)
             render_kwargs_train["network_fine"] = self.fine_model
         dev = target_s.device
-        latent_table = torch.stack(self.latents, dim=0).to(dev)                      # [T, Z]
         key = tuple(dataset_extras["imageid_to_timestepid"])
         if getattr(self, "_i2t", (None, None))[0] != (key, dev):   # one H2D copy, not one per step (train.py:178-180)
             self._i2t = ((key, dev), torch.as_tensor(dataset_extras["imageid_to_timestepid"], device=dev))
         imageid_to_timestepid = self._i2t[1]
-        n_rays = rays_o.shape[0]
         timestep = imageid_to_timestepid[batch_pixel_indices[:, 0].to(dev).long()]
-        # [N, Z]; index_select (backward = one index_add_) instead of advanced indexing (backward = sort-based index_put_)
-        info = {"ray_bending_latents": torch.index_select(latent_table, 0, timestep)}
+        # [N, Z] per-ray latents (train.py:173-189).  The per-frame latents are read in place (they are views of the
+        # optimizer's flat buffer) and their gradient is one index_add_ into the .grad arena.
+        info = {"ray_bending_latents": _ag.gather_latents(self.latents, timestep)}
         detailed = args.offsets_loss_weight > 0.0 or args.divergence_loss_weight > 0.0
         rgb, disp, acc, extras = T.render(rays_o, rays_d, chunk=args.chunk, verbose=i < 10, retraw=True,
                                           additional_pixel_information=info, detailed_output=detailed, **render_kwargs_train)
-        sched = (1.0 / 100.0) ** (1 - (global_step / args.N_iters))                   # increasing schedule
+        # increasing schedule of the regularisers (train.py:229, :281).  `global_step` may be a 0-dim CUDA tensor: the
+        # schedule is then evaluated on the device, so a step captured in a CUDA graph follows it when replayed.
+        if isinstance(global_step, torch.Tensor):
+            sched = torch.pow(torch.full((), 0.01, dtype=torch.float32, device=dev), 1.0 - global_step.float() / float(args.N_iters))
+            lam_o, lam_o_scale = args.offsets_loss_weight, sched
+        else:
+            sched = (1.0 / 100.0) ** (1 - (global_step / args.N_iters))
+            lam_o, lam_o_scale = args.offsets_loss_weight * sched, None
         use_offsets = self.ray_bender is not None and args.offsets_loss_weight > 0.0
         # data term (fine + coarse) and offsets / rigidity regulariser (train.py:208-242) in one fused kernel
         loss = _ag.ray_loss(rgb, extras.get("rgb0"), target_s,
                             extras["visibility_weights"] if use_offsets else None,
                             extras["unmasked_offsets"] if use_offsets else None,
                             extras["rigidity_mask"] if use_offsets else None,
-                            args.offsets_loss_weight * sched if use_offsets else 0.0, args.rigidity_loss_weight)
+                            lam_o if use_offsets else 0.0, args.rigidity_loss_weight,
+                            lam_o_scale if use_offsets else None)
         if self.ray_bender is not None and args.divergence_loss_weight > 0.0:
             # exact_divergence = False, backprop_into_weights = False (train.py:246-247); fused closed-form kernel
             # weights 1 - exp(-relu(opacity_alpha)) (train.py:267) are formed inside the kernels
+            # Hutchinson probes: torch.randn like run_nerf_helpers.py:110, or injected with the other random draws
+            # (render_kwargs_train["randomness"]["e"], [N * N_samples, 3]) for exact reproduction
+            rnd = render_kwargs_train.get("randomness")
+            probes = rnd.get("e") if isinstance(rnd, dict) else None
             div = _ag.divergence_loss(extras["unmasked_offsets"], extras["rigidity_mask"], None, self.ray_bender,
-                                      opacity_alpha=extras["opacity_alpha"])
-            loss = loss + args.divergence_loss_weight * sched * div
+                                      e=None if probes is None else probes.to(dev), opacity_alpha=extras["opacity_alpha"])
+            loss = loss + (args.divergence_loss_weight * sched) * div
         return loss
 
 
@@ -267,6 +320,9 @@ class render_wrapper_class(torch.nn.Module):
 
 
 def get_parallelized_training_function(coarse_model, latents, fine_model=None, ray_bender=None):
+    _register_sharded_params(list(latents) + list(coarse_model.parameters())
+                             + (list(fine_model.parameters()) if fine_model is not None else [])
+                             + (list(ray_bender.parameters()) if ray_bender is not None else []))
     _install_optimizer_hook()
     return RayShardedFunction(training_wrapper_class(coarse_model, latents, fine_model=fine_model, ray_bender=ray_bender))
 

@@ -333,6 +333,24 @@ def divergence_loss(bp, ret: Dict[str, Tensor], latents: Tensor, n_rays: int, s_
     return torch.mean((w * torch.abs(div) ** 2).view(n_rays, -1), dim=-1)
 
 
+def training_wrapper_loss(cp, fp, bp, rays: Dict[str, Tensor], latent_table: Tensor, imageid_to_timestepid, pixel_indices: Tensor,
+                          rnd: Dict[str, Tensor], e: Tensor, global_step: int, n_iters: int, offsets_w: float,
+                          divergence_w: float, rigidity_w: float, s_c: int = 64, n_imp: int = 64):
+    """Per-ray loss [N] of training_wrapper_class.forward (train.py:152-287): latent lookup by the ray's image id
+    (:173-189), training-mode render, data terms, offsets / rigidity regulariser and divergence regulariser, both
+    scaled by the increasing schedule (1/100)^(1 - global_step / N_iters) (:229, :281).  Returns (loss, ret)."""
+    n = rays["rays_o"].shape[0]
+    i2t = torch.as_tensor(imageid_to_timestepid)
+    lat = latent_table[i2t[pixel_indices[:, 0]], :]
+    ret = render_rays(cp, fp, bp, rays["rays_o"], rays["rays_d"], rays["near"], rays["far"], lat, s_c, n_imp, perturb=True,
+                      raw_noise_std=1.0, rnd=rnd)
+    sched = (1.0 / 100.0) ** (1 - (global_step / n_iters))
+    loss = training_loss(ret, rays["target"], offsets_w, rigidity_w, sched)
+    if divergence_w > 0.0:
+        loss = loss + divergence_w * sched * divergence_loss(bp, ret, lat, n, s_c, e)
+    return loss, ret
+
+
 def clone_params(p, requires_grad=False):
     out = {}
     for k, v in p.items():

@@ -239,6 +239,75 @@ def main():
                                            detailed_output=True, retraw=True, **kw)
     np.savez_compressed(os.path.join(outdir, "caseF_canonical.npz"), seed=seed, n=n, rgb_map=np32(rgb), disp_map=np32(disp),
                         acc_map=np32(acc), rgb0=np32(extras["rgb0"]), keys=np.array(sorted(extras.keys())))
+
+    # ---------------- case G + H: the training wrapper DataParallel wraps (train.py:140-287) -----------
+    # H: per-ray loss [N] of the unmodified training_wrapper_class.forward with all three regularisers, its gradients,
+    # and (G) the divergence term alone (compute_divergence_loss, run_nerf_helpers.py:22-116) with the Hutchinson
+    # probes `e` recorded from the reference's own torch.randn_like call (recorded, not replaced: the arithmetic is the
+    # reference's; the oracle and the kernels get the same e injected).
+    seed, n, n_img = 700, 96, 7
+    coarse, fine, bender, kw, _ = build_reference_models(rt, rh, O, seed)
+    rays = O.make_rays(seed, n)
+    lat_rs = np.random.RandomState(seed + 11)
+    latent_list = [torch.from_numpy((lat_rs.randn(32) * 0.1).astype(np.float32)).requires_grad_(True) for _ in range(n_img)]
+    pix = np.stack([lat_rs.randint(0, n_img, size=n), lat_rs.randint(0, 384, size=n), lat_rs.randint(0, 512, size=n)], -1)
+    pix = torch.from_numpy(pix.astype(np.int64))
+    i2t = [int(v) for v in lat_rs.permutation(n_img)]       # image id -> time-step id (a permutation: exercises the lookup)
+    targs = types.SimpleNamespace(chunk=32768, N_samples=64, N_importance=64, N_iters=200000, offsets_loss_weight=60.0,
+                                  divergence_loss_weight=3.0, rigidity_loss_weight=0.0005, ray_bending_latent_size=32)
+    global_step = 50000
+    kwh = dict(kw); kwh["perturb"] = 1.0; kwh["raw_noise_std"] = 1.0
+    kwh["near"], kwh["far"] = rays["near"], rays["far"]
+    wrapper = rt.training_wrapper_class(coarse, latent_list, fine_model=fine, ray_bender=bender)
+    recorded = []
+    _orig_randn_like = torch.randn_like
+
+    def recording_randn_like(t, *a, **k):
+        out = _orig_randn_like(t, *a, **k)
+        recorded.append(out.detach().clone())
+        return out
+
+    torch.manual_seed(seed)
+    torch.randn_like = recording_randn_like
+    try:
+        loss = wrapper(targs, rays["rays_o"], rays["rays_d"], 100, kwh, rays["target"], global_step, 0,
+                       {"imageid_to_timestepid": i2t}, pix)
+    finally:
+        torch.randn_like = _orig_randn_like
+    assert len(recorded) == 1 and recorded[0].shape == (n * 64, 3)
+    e = recorded[0]
+    loss.mean().backward()
+    named = [("coarse." + k, v) for k, v in coarse.named_parameters()] + \
+            [("fine." + k, v) for k, v in fine.named_parameters()] + \
+            [("bender." + k, v) for k, v in bender.named_parameters()]
+    save = dict(seed=seed, n=n, n_img=n_img, pix=pix.numpy(), i2t=np.asarray(i2t, dtype=np.int64), global_step=global_step,
+                N_iters=targs.N_iters, offsets_w=targs.offsets_loss_weight, divergence_w=targs.divergence_loss_weight,
+                rigidity_w=targs.rigidity_loss_weight, loss=np32(loss), e=np32(e),
+                latent_table=np.stack([np32(l) for l in latent_list]),
+                latent_grads=np.stack([np32(l.grad) if l.grad is not None else np.zeros(32, np.float32) for l in latent_list]))
+    save.update(grad_summary(named))
+    np.savez_compressed(os.path.join(outdir, "caseH_training_wrapper.npz"), **save)
+
+    # G: the divergence term on its own, same models / rays / probes, deterministic render (perturb = 0, no noise)
+    for m in (coarse, fine, bender):
+        m.zero_grad()
+    lat_rows = torch.stack([l.detach() for l in latent_list], 0)[torch.tensor(i2t)[pix[:, 0]]].clone().requires_grad_(True)
+    kwg = dict(kw); kwg["near"], kwg["far"] = rays["near"], rays["far"]
+    rgb, disp, acc, extras = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, retraw=True,
+                                       additional_pixel_information={"ray_bending_latents": lat_rows}, detailed_output=True, **kwg)
+    wdiv = 1.0 - torch.exp(-torch.nn.functional.relu(extras["opacity_alpha"].view(-1)))
+    dlat = lat_rows.view(n, 1, -1).expand(n, 64, 32).reshape(-1, 32)
+    torch.randn_like = lambda t, *a, **k: e.clone()
+    try:
+        div = rh.compute_divergence_loss(extras["masked_offsets"].view(-1, 3), extras["initial_input_pts"].view(-1, 3), dlat, bender,
+                                         exact=False, chunk=32768, N_rays=n, weights=wdiv, backprop_into_weights=False)
+    finally:
+        torch.randn_like = _orig_randn_like
+    div.mean().backward()
+    named = [("bender." + k, v) for k, v in bender.named_parameters()]
+    save = dict(seed=seed, n=n, div=np32(div), e=np32(e), latents=np32(lat_rows), latents_grad=np32(lat_rows.grad))
+    save.update(grad_summary(named))
+    np.savez_compressed(os.path.join(outdir, "caseG_divergence.npz"), **save)
     print("golden vectors written to", outdir)
 
 

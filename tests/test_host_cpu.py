@@ -135,8 +135,16 @@ def _worker(rank, world, port, n, out_path, uniform):
     net = torch.nn.Sequential(torch.nn.Linear(5, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
     dead = torch.nn.Parameter(torch.zeros(3))            # never used: its grad must stay None on every rank
     opt = torch.optim.Adam(list(net.parameters()) + [dead], lr=1e-2)
+    P._register_sharded_params(list(net.parameters()) + [dead])   # what get_parallelized_training_function does
     P._install_optimizer_hook()
     fn = P.RayShardedFunction(_ToyStep(net))
+    # an unrelated optimizer in the same process (bench.py's CPU baseline, a user's second model) must not be drawn into
+    # the collective: only rank 0 steps it -- if the hook all-reduced its gradients, rank 1 would never answer
+    other = torch.nn.Linear(3, 1)
+    other_opt = torch.optim.Adam(other.parameters(), lr=1e-2)
+    if rank == 0:
+        other(torch.ones(2, 3)).sum().backward()
+        other_opt.step()
     g = torch.Generator().manual_seed(7 + rank)          # ranks draw DIFFERENT batches; rank 0's must win
     for it in range(3):
         rays, lat, tgt = torch.randn(n, 3, generator=g), torch.randn(n, 2, generator=g), torch.randn(n, 3, generator=g)

@@ -142,6 +142,57 @@ def test_caseF_canonical():
     assert ref_keys == ours, (ref_keys ^ ours)
 
 
+def _bender_grad_checks(g, bp, rtol):
+    for i in range(5):
+        nm = f"bender.network.{i}.weight"
+        gr = bp["net_w"][i].grad.reshape(-1)
+        close(gr[torch.from_numpy(g[nm + ".idx"])], g[nm + ".val"], 1e-7, rtol, name=nm)
+        assert abs(float(gr.norm()) - float(g[nm + ".norm"][0])) <= rtol * float(g[nm + ".norm"][0]) + 1e-9, nm
+    for i in range(3):
+        nm = f"bender.rigidity_network.{i}.weight"
+        gr = bp["rig_w"][i].grad.reshape(-1)
+        close(gr[torch.from_numpy(g[nm + ".idx"])], g[nm + ".val"], 1e-7, rtol, name=nm)
+
+
+def test_caseG_divergence_regulariser():
+    """compute_divergence_loss / divergence_approx (run_nerf_helpers.py:22-116) with the probes the reference drew."""
+    g = load("caseG_divergence.npz")
+    seed, n = int(g["seed"]), int(g["n"])
+    cp, fp, bp = models(seed)
+    bp = O.clone_params(bp, True)
+    r = O.make_rays(seed, n)
+    lat = torch.from_numpy(g["latents"]).clone().requires_grad_(True)
+    ret = O.render_rays(cp, fp, bp, r["rays_o"], r["rays_d"], r["near"], r["far"], lat, 64, 64)
+    div = O.divergence_loss(bp, ret, lat, n, 64, torch.from_numpy(g["e"]))
+    close(div, g["div"], 1e-9, 2e-4, name="div")
+    div.mean().backward()
+    close(lat.grad, g["latents_grad"], 1e-9, 2e-3, name="latents_grad")
+    _bender_grad_checks(g, bp, 2e-3)
+
+
+def test_caseH_training_wrapper_loss_and_grads():
+    """The per-ray loss [N] DataParallel gathers (training_wrapper_class.forward, train.py:152-287), all regularisers on."""
+    g = load("caseH_training_wrapper.npz")
+    seed, n = int(g["seed"]), int(g["n"])
+    cp, fp, bp = models(seed)
+    cp, fp, bp = O.clone_params(cp, True), O.clone_params(fp, True), O.clone_params(bp, True)
+    r = O.make_rays(seed, n)
+    rnd = O.make_randomness(seed, n, 64, 64)
+    table = torch.from_numpy(g["latent_table"]).clone().requires_grad_(True)
+    loss, _ = O.training_wrapper_loss(cp, fp, bp, r, table, g["i2t"], torch.from_numpy(g["pix"]), rnd, torch.from_numpy(g["e"]),
+                                      int(g["global_step"]), int(g["N_iters"]), float(g["offsets_w"]), float(g["divergence_w"]),
+                                      float(g["rigidity_w"]))
+    close(loss, g["loss"], 2e-6, 2e-5, name="loss")
+    loss.mean().backward()
+    close(table.grad, g["latent_grads"], 1e-8, 2e-3, name="latent_grads")
+    for net, p in {"coarse": cp, "fine": fp}.items():
+        for i in (0, 4, 5, 7):
+            nm = f"{net}.pts_linears.{i}.weight"
+            gr = p["pts_w"][i].grad.reshape(-1)
+            close(gr[torch.from_numpy(g[nm + ".idx"])], g[nm + ".val"], 1e-7, 2e-3, name=nm)
+    _bender_grad_checks(g, bp, 2e-3)
+
+
 def test_flop_ledger():
     cp = O.make_nerf_params(0)
     bp = O.make_bender_params(0)
