@@ -308,6 +308,8 @@ def main():
             from nonrigid_nerf_b200.graphs import GraphedStep
             graphed = GraphedStep(local_step, resident[0], warmup=3)
         except Exception as exc:  # noqa: BLE001 - fall back to the eager loop, and say so in the JSON line
+            import traceback
+            traceback.print_exc()
             print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
             graphed = None
             torch.cuda.synchronize()

@@ -47,6 +47,20 @@ int nrn_pack_bender(const float* const* net_w /*5*/, const float* const* net_b /
                     const float* const* rig_w /*3*/, const float* const* rig_b /*3*/, int latent_size,
                     void* packed, void* stream);
 
+/* ---- ray generation: get_rays / get_rays_np (run_nerf_helpers.py:588-622) on the device -----------------------------
+ * c2w [3][4] row-major, intrinsics = (focal_x, focal_y, center_x, center_y); rays_o / rays_d [H*W][3] in the [H, W, 3]
+ * order of the reference.  Bit-identical to the reference's float32 arithmetic. */
+int nrn_get_rays(const float* c2w, const float* intrinsics, int height, int width, float* rays_o, float* rays_d, void* stream);
+/* A training batch computed on demand instead of gathered from the host table of every ray of every image
+ * (train.py:1498-1517, :1546-1564): pix [n][3] int64 = (image, x, y) as in batch_pixel_indices; poses [n_images][3][4];
+ * intrinsics [n_views][4]; image_to_view [n_images] int32 or NULL (single view); images [n_images][H][W][3] fp32 or NULL
+ * (then target may be NULL). */
+int nrn_ray_batch(const int64_t* pix, int n, const float* poses, const float* intrinsics, const int32_t* image_to_view,
+                  const float* images, int height, int width, float* rays_o, float* rays_d, float* target, void* stream);
+/* ---- free-viewpoint post-processing, free_viewpoint_rendering.py:623-629: per ray the index of the sample whose
+ * accumulated visibility weight is closest to 0.5 (first minimum).  weights [n][n_samples] -> index [n] int64. */
+int nrn_median_visibility_index(const float* weights, int n_rays, int n_samples, int64_t* index, void* stream);
+
 /* ---- coarse depth sampling: render_rays, train.py:847-869 ------------------------------------
  * rays [n][8] = (o, d, near, far); t_rand [n][S] uniform randoms or NULL (perturb == 0). */
 int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_samples, int lindisp,

@@ -164,6 +164,33 @@ int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "sample_coarse_kernel");
 }
 
+int nrn_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, float* rays_d, void* stream) {
+  if (H < 0 || W < 0) return fail(NRN_E_INVALID, "nrn_get_rays: bad sizes");
+  if (H == 0 || W == 0) return NRN_OK;
+  if (!c2w || !K || !rays_o || !rays_d) return fail(NRN_E_INVALID, "nrn_get_rays: null argument");
+  const cudaError_t e = nrn::launch_get_rays(c2w, K, H, W, rays_o, rays_d, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "get_rays_kernel");
+}
+
+int nrn_ray_batch(const int64_t* pix, int n, const float* poses, const float* K, const int32_t* image_to_view, const float* images,
+                  int H, int W, float* rays_o, float* rays_d, float* target, void* stream) {
+  if (n < 0 || H < 1 || W < 1) return fail(NRN_E_INVALID, "nrn_ray_batch: bad sizes");
+  if (n == 0) return NRN_OK;
+  if (!pix || !poses || !K || !rays_o || !rays_d || (images && !target)) return fail(NRN_E_INVALID, "nrn_ray_batch: null argument");
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  const cudaError_t e = nrn::launch_ray_batch(reinterpret_cast<const long long*>(pix), n, poses, K, image_to_view, images, H, W, rays_o, rays_d,
+                                              target, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_batch_kernel");
+}
+
+int nrn_median_visibility_index(const float* weights, int n_rays, int n_samples, int64_t* index, void* stream) {
+  if (n_rays < 0 || n_samples < 1) return fail(NRN_E_INVALID, "nrn_median_visibility_index: bad sizes");
+  if (n_rays == 0) return NRN_OK;
+  if (!weights || !index) return fail(NRN_E_INVALID, "nrn_median_visibility_index: null argument");
+  const cudaError_t e = nrn::launch_median_index(weights, n_rays, n_samples, reinterpret_cast<long long*>(index), static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "median_index_kernel");
+}
+
 int nrn_field_forward(const NrnFieldArgs* a) {
   if (!a) return fail(NRN_E_INVALID, "nrn_field_forward: null args");
   if (a->n_rays < 0 || a->n_samples < 1) return fail(NRN_E_INVALID, "nrn_field_forward: bad sizes n=%d S=%d", a->n_rays, a->n_samples);

@@ -330,6 +330,93 @@ composite_bwd_kernel(const CompositeBwdParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ray generation (get_rays / get_rays_np, run_nerf_helpers.py:588-622) for whole frames or for a random batch of
+// (image, x, y) pixels (train.py:1498-1517 builds a host table of every ray of every image and train.py:1546-1564
+// gathers N_rand rows of it per step; here the rows are computed on demand from the 3x4 poses and the intrinsics).
+//   dirs = [(x - cx) / fx, -(y - cy) / fy, -1];  rays_d[r] = dirs . c2w[r, :3]  (sum over the three products in index
+//   order, no FMA contraction: bit-identical to numpy's / torch's float32 evaluation);  rays_o = c2w[:, 3]
+__device__ __forceinline__ void ray_from_pixel(const float* __restrict__ c2w, const float* __restrict__ K, float x, float y,
+                                               float* __restrict__ o, float* __restrict__ d) {
+  const float dx = __fdiv_rn(__fsub_rn(x, K[2]), K[0]);
+  const float dy = -__fdiv_rn(__fsub_rn(y, K[3]), K[1]);
+  const float dz = -1.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    d[r] = __fadd_rn(__fadd_rn(__fmul_rn(dx, c2w[r * 4 + 0]), __fmul_rn(dy, c2w[r * 4 + 1])), __fmul_rn(dz, c2w[r * 4 + 2]));
+    o[r] = c2w[r * 4 + 3];
+  }
+}
+
+// one frame: pixel (row j, column i) -> ray j * W + i  (the [H, W, 3] layout of get_rays)
+__global__ void get_rays_kernel(const float* __restrict__ c2w, const float* __restrict__ K, int H, int W, float* __restrict__ rays_o,
+                                float* __restrict__ rays_d) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(H) * W) return;
+  const int j = static_cast<int>(idx / W), i = static_cast<int>(idx - static_cast<long long>(j) * W);
+  float o[3], d[3];
+  ray_from_pixel(c2w, K, static_cast<float>(i), static_cast<float>(j), o, d);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { rays_o[idx * 3 + r] = o[r]; rays_d[idx * 3 + r] = d[r]; }
+}
+
+// a training batch: pix [n][3] = (image, x, y) int64 (the reference's batch_pixel_indices); poses [n_img][3][4];
+// intrinsics [n_views][4] = (fx, fy, cx, cy), view of an image through image_to_view (or view 0 when null);
+// images [n_img][H][W][3] fp32 -> target [n][3]
+__global__ void ray_batch_kernel(const long long* __restrict__ pix, int n, const float* __restrict__ poses, const float* __restrict__ K,
+                                 const int* __restrict__ image_to_view, const float* __restrict__ images, int H, int W,
+                                 float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ target) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const long long img = pix[idx * 3 + 0], x = pix[idx * 3 + 1], y = pix[idx * 3 + 2];
+  const int view = image_to_view ? image_to_view[img] : 0;
+  float o[3], d[3];
+  ray_from_pixel(poses + img * 12, K + view * 4, static_cast<float>(x), static_cast<float>(y), o, d);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { rays_o[idx * 3 + r] = o[r]; rays_d[idx * 3 + r] = d[r]; }
+  if (images && target) {
+    const float* px = images + ((img * H + y) * W + x) * 3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) target[idx * 3 + r] = px[r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Free-viewpoint post-processing (free_viewpoint_rendering.py:623-629): per pixel the sample whose accumulated
+// visibility is closest to 0.5 -- "most likely on the visible surface".  cumsum in index order (one thread per ray, the
+// order of a sequential cumsum), first minimum wins like torch.min.
+__global__ void median_index_kernel(const float* __restrict__ w, int n, int S, long long* __restrict__ idx_out) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n) return;
+  const float* row = w + static_cast<long long>(ray) * S;
+  float acc = 0.f, best = 3.0e38f;
+  int arg = 0;
+  for (int i = 0; i < S; ++i) {
+    acc = __fadd_rn(acc, row[i]);
+    const float dist = fabsf(__fsub_rn(acc, 0.5f));
+    if (dist < best) { best = dist; arg = i; }
+  }
+  idx_out[ray] = arg;
+}
+
+cudaError_t launch_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, float* rays_d, cudaStream_t st) {
+  const long long total = static_cast<long long>(H) * W;
+  if (total == 0) return cudaSuccess;
+  get_rays_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(c2w, K, H, W, rays_o, rays_d);
+  return cudaGetLastError();
+}
+cudaError_t launch_ray_batch(const long long* pix, int n, const float* poses, const float* K, const int* image_to_view,
+                             const float* images, int H, int W, float* rays_o, float* rays_d, float* target, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  ray_batch_kernel<<<(n + 255) / 256, 256, 0, st>>>(pix, n, poses, K, image_to_view, images, H, W, rays_o, rays_d, target);
+  return cudaGetLastError();
+}
+cudaError_t launch_median_index(const float* w, int n, int S, long long* idx, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  median_index_kernel<<<(n + 127) / 128, 128, 0, st>>>(w, n, S, idx);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 cudaError_t launch_sample_coarse(const float* rays, const float* t_rand, int n, int S, int lindisp, float* z_out,
                                  cudaStream_t st) {
   const long long total = static_cast<long long>(n) * S;

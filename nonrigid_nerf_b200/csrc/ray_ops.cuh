@@ -42,5 +42,9 @@ cudaError_t launch_composite(const CompositeParams& p, cudaStream_t st);
 cudaError_t launch_sample_pdf(const float* bins, const float* weights, const float* u, int n, int nb, int n_samp,
                               float* out, cudaStream_t st);
 cudaError_t launch_composite_bwd(const CompositeBwdParams& p, cudaStream_t st);
+cudaError_t launch_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, float* rays_d, cudaStream_t st);
+cudaError_t launch_ray_batch(const long long* pix, int n, const float* poses, const float* K, const int* image_to_view,
+                             const float* images, int H, int W, float* rays_o, float* rays_d, float* target, cudaStream_t st);
+cudaError_t launch_median_index(const float* w, int n, int S, long long* idx, cudaStream_t st);
 
 }  // namespace nrn

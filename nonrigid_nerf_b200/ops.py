@@ -289,3 +289,61 @@ def sample_pdf_op(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: 
     with torch.cuda.device(bins.device):
         _lib.check(_lib.load().nrn_sample_pdf(_ptr(bins), _ptr(weights), _ptr(u), n, nb, n_samples, _ptr(out), _stream()), "sample_pdf")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# ray generation, batch sampling, free-viewpoint post-processing
+# ---------------------------------------------------------------------------------------------
+def intrinsics_row(intrin) -> list:
+    return [float(intrin["focal_x"]), float(intrin["focal_y"]), float(intrin["center_x"]), float(intrin["center_y"])]
+
+
+def get_rays(c2w: torch.Tensor, intrin) -> Tuple[torch.Tensor, torch.Tensor]:
+    """get_rays (run_nerf_helpers.py:588-605): rays_o, rays_d [H, W, 3] of one camera, computed on the device."""
+    if not c2w.is_cuda:
+        raise RuntimeError("nonrigid_nerf_b200: get_rays needs a CUDA pose (there is no CPU path)")
+    h, w = int(intrin["height"]), int(intrin["width"])
+    pose = c2w[:3, :4].float().contiguous()
+    k = torch.tensor(intrinsics_row(intrin), dtype=torch.float32, device=c2w.device)
+    rays_o = torch.empty(h, w, 3, dtype=torch.float32, device=c2w.device)
+    rays_d = torch.empty(h, w, 3, dtype=torch.float32, device=c2w.device)
+    with torch.cuda.device(c2w.device):
+        _lib.check(_lib.load().nrn_get_rays(_ptr(pose), _ptr(k), h, w, _ptr(rays_o), _ptr(rays_d), _stream()), "get_rays")
+    return rays_o, rays_d
+
+
+def ray_batch(pix: torch.Tensor, poses: torch.Tensor, intrinsics: torch.Tensor, image_to_view: Optional[torch.Tensor],
+              images: Optional[torch.Tensor], height: int, width: int):
+    """Rays (and target colours) of the pixels pix [N, 3] = (image, x, y), computed from poses [n_img, 3, 4] and
+    intrinsics [n_views, 4] instead of gathered from a table of every ray (train.py:1498-1517, :1546-1564)."""
+    for t, nm in ((pix, "pix"), (poses, "poses"), (intrinsics, "intrinsics")):
+        if not t.is_cuda:
+            raise RuntimeError(f"nonrigid_nerf_b200: ray_batch needs CUDA tensors ({nm}); there is no CPU path")
+    n = pix.shape[0]
+    dev = pix.device
+    pix = pix.long().contiguous()
+    poses = poses[:, :3, :4].float().contiguous()
+    intrinsics = intrinsics.float().contiguous()
+    if image_to_view is not None:
+        image_to_view = image_to_view.to(dev).int().contiguous()
+    rays_o = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    rays_d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    target = None
+    if images is not None:
+        if images.dtype != torch.float32 or not images.is_contiguous() or tuple(images.shape[1:]) != (height, width, 3):
+            raise RuntimeError("nonrigid_nerf_b200: ray_batch images must be a contiguous fp32 [n_images, H, W, 3] CUDA tensor")
+        target = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().nrn_ray_batch(_ptr(pix), n, _ptr(poses), _ptr(intrinsics), _ptr(image_to_view), _ptr(images), height, width,
+                                             _ptr(rays_o), _ptr(rays_d), _ptr(target), _stream()), "ray_batch")
+    return rays_o, rays_d, target
+
+
+def median_visibility_index(weights: torch.Tensor) -> torch.Tensor:
+    """Index [N] (int64) of the sample whose accumulated visibility is closest to 0.5 (free_viewpoint_rendering.py:623-629)."""
+    weights = _f32c(weights, "weights")
+    n, s = weights.shape
+    idx = torch.empty(n, dtype=torch.int64, device=weights.device)
+    with torch.cuda.device(weights.device):
+        _lib.check(_lib.load().nrn_median_visibility_index(_ptr(weights), n, s, _ptr(idx), _stream()), "median_visibility_index")
+    return idx

@@ -171,6 +171,13 @@ class NeRF(nn.Module):
         return raw
 
 
+# ---- ray helpers (run_nerf_helpers.py:588-605) ------------------------------------------------------------
+def get_rays(c2w, intrin):
+    """rays_o, rays_d [H, W, 3] of the camera c2w [3(+), 4] with intrinsics intrin (dict: height, width, focal_x, focal_y,
+    center_x, center_y) -- one kernel, bit-identical to the reference's float32 arithmetic."""
+    return ops.get_rays(c2w, intrin)
+
+
 # ---- hierarchical sampling (run_nerf_helpers.py:651-698) ------------------------------------------
 def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
     if pytest:

@@ -137,8 +137,22 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     else:
         c0 = None
         c1 = _ag.composite(raw, z_vals, rays_d, noise, white_bkgd)
+        z_fine, run_fn = z_vals, network_fn
 
     ret = {"rgb_map": c1["rgb_map"], "disp_map": c1["disp_map"], "acc_map": c1["acc_map"]}
+    if dummy_kwargs.get("surface_output", False):
+        # Fused free-viewpoint post-processing (free_viewpoint_rendering.py:617-658): instead of shipping every sample's
+        # bent point and rigidity to the host (11.5 KB per ray) and indexing there, pick the median-visibility sample on
+        # the device and evaluate the bender for that ONE point per ray: 4 floats + an index per ray.
+        with torch.no_grad():
+            idx = ops.median_visibility_index(c1["weights"])
+            z_s = torch.gather(z_fine, 1, idx[:, None])
+            pts = rays[:, 0:3] + rays[:, 3:6] * z_s          # multiply, then add: the same rounding as the field kernel
+            _, det = _ag.field_points(run_fn, pts, latents, True)
+        ret["median_indices"] = idx
+        ret["surface_pts"] = det["input_pts"].reshape(n, 3)
+        if "rigidity_mask" in det:
+            ret["surface_rigidity"] = det["rigidity_mask"].reshape(n)
     if retraw:
         ret["raw"] = raw
     if N_importance > 0:
@@ -196,3 +210,36 @@ def render(rays_o, rays_d, chunk=1024 * 32, ndc=True, near=0.0, far=1.0, use_vie
     ret_list = [all_ret[k] for k in k_extract]
     ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
     return ret_list + [ret_dict]
+
+
+# ---- batch sampling of the training loop (train.py:1498-1517, :1546-1564) on the device ------------------------------
+class RayBatchSampler:
+    """Keeps the images, poses and intrinsics resident on the GPU and produces a training batch -- random (image, x, y)
+    pixels, their rays and target colours -- with one kernel, instead of gathering rows of a host-side table of every ray
+    of every image (0.8 GB for the example sequence) and copying them to the device each iteration.
+
+        sampler = RayBatchSampler(images, poses, intrinsics, dataset_extras["imageid_to_viewid"], device)
+        batch_rays, target_s, batch_pixel_indices = sampler.sample(N_rand)        # [2, N, 3], [N, 3], [N, 3] (image, x, y)
+
+    `generator` (a torch.Generator on the device) makes the draw reproducible and identical across ranks."""
+
+    def __init__(self, images, poses, intrinsics, imageid_to_viewid=None, device="cuda"):
+        dev = torch.device(device)
+        self.images = torch.as_tensor(images, dtype=torch.float32).to(dev).contiguous()          # [n_img, H, W, 3]
+        self.poses = torch.as_tensor(poses, dtype=torch.float32)[:, :3, :4].to(dev).contiguous()
+        self.n_images, self.height, self.width = self.images.shape[0], self.images.shape[1], self.images.shape[2]
+        if int(intrinsics[0]["height"]) != self.height or int(intrinsics[0]["width"]) != self.width:
+            raise RuntimeError("nonrigid_nerf_b200: intrinsics do not match the image size")
+        self.intrinsics = torch.tensor([ops.intrinsics_row(k) for k in intrinsics], dtype=torch.float32, device=dev)
+        self.image_to_view = None if imageid_to_viewid is None else torch.as_tensor(list(imageid_to_viewid), dtype=torch.int32, device=dev)
+
+    def sample(self, n_rand: int, generator=None):
+        dev = self.images.device
+        pix = torch.stack([torch.randint(self.n_images, (n_rand,), device=dev, generator=generator),
+                           torch.randint(self.width, (n_rand,), device=dev, generator=generator),
+                           torch.randint(self.height, (n_rand,), device=dev, generator=generator)], -1)    # (image, x, y)
+        return self.rays_for(pix)
+
+    def rays_for(self, pix: torch.Tensor):
+        rays_o, rays_d, target = ops.ray_batch(pix, self.poses, self.intrinsics, self.image_to_view, self.images, self.height, self.width)
+        return torch.stack([rays_o, rays_d], 0), target, pix

@@ -351,6 +351,29 @@ def training_wrapper_loss(cp, fp, bp, rays: Dict[str, Tensor], latent_table: Ten
     return loss, ret
 
 
+def get_rays(c2w: Tensor, intrin) -> Tuple[Tensor, Tensor]:
+    """get_rays / get_rays_np (run_nerf_helpers.py:588-622): rays_o, rays_d [H, W, 3] float32."""
+    h, w = int(intrin["height"]), int(intrin["width"])
+    i, j = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32), indexing="xy")
+    dirs = np.stack([(i - np.float32(intrin["center_x"])) / np.float32(intrin["focal_x"]),
+                     -(j - np.float32(intrin["center_y"])) / np.float32(intrin["focal_y"]), -np.ones_like(i)], -1)
+    c = c2w.numpy().astype(np.float32)
+    rays_d = np.sum(dirs[..., np.newaxis, :] * c[:3, :3], -1)
+    rays_o = np.broadcast_to(c[:3, -1], np.shape(rays_d))
+    return torch.from_numpy(np.ascontiguousarray(rays_o)), torch.from_numpy(rays_d.astype(np.float32))
+
+
+def surface_selection(weights: Tensor, input_pts: Tensor, rigidity: Optional[Tensor]):
+    """free_viewpoint_rendering.py:623-651: per ray the sample whose accumulated visibility is closest to 0.5, and the
+    canonical point / rigidity at that sample.  weights [N,S], input_pts [N,S,3], rigidity [N,S(,1)]."""
+    acc = torch.cumsum(weights, dim=-1)
+    idx = torch.min(torch.abs(acc - 0.5), dim=-1)[1]
+    rows = torch.arange(weights.shape[0])
+    pts = input_pts[rows, idx, :]
+    rig = rigidity.reshape(weights.shape[0], -1)[rows, idx] if rigidity is not None else None
+    return idx, pts, rig
+
+
 def clone_params(p, requires_grad=False):
     out = {}
     for k, v in p.items():

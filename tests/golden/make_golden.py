@@ -308,6 +308,34 @@ def main():
     save = dict(seed=seed, n=n, div=np32(div), e=np32(e), latents=np32(lat_rows), latents_grad=np32(lat_rows.grad))
     save.update(grad_summary(named))
     np.savez_compressed(os.path.join(outdir, "caseG_divergence.npz"), **save)
+
+    # ---------------- case I: ray generation (run_nerf_helpers.py:588-622) ------------------------------
+    rs = np.random.RandomState(31)
+    intrin = {"height": 24, "width": 40, "focal_x": 31.7, "focal_y": 30.9, "center_x": 19.3, "center_y": 12.4}
+    q, _ = np.linalg.qr(rs.randn(3, 3))
+    c2w = np.concatenate([q, rs.randn(3, 1) * 0.3], 1).astype(np.float32)
+    ro_np, rd_np = rh.get_rays_np(c2w, intrin)
+    ro_t, rd_t = rh.get_rays(torch.from_numpy(c2w), intrin)
+    assert np.array_equal(rd_np.astype(np.float32), rd_t.numpy()), "get_rays and get_rays_np disagree"
+    np.savez_compressed(os.path.join(outdir, "caseI_get_rays.npz"), c2w=c2w, rays_o=np32(ro_t), rays_d=np32(rd_t),
+                        **{k: np.float64(v) for k, v in intrin.items()})
+
+    # ---------------- case J: free-viewpoint surface selection (free_viewpoint_rendering.py:617-658) -----
+    # the reference does this inline in a script function; the lines are executed here on a reference render
+    seed, n = 800, 192
+    coarse, fine, bender, kw, _ = build_reference_models(rt, rh, O, seed)
+    rays = O.make_rays(seed, n)
+    lat_one = rays["latents"][:1].expand(n, 32)          # render_path: one latent for the whole frame (train.py:465)
+    with torch.no_grad():
+        rgb, disp, acc, det = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, near=rays["near"], far=rays["far"],
+                                        additional_pixel_information={"ray_bending_latents": lat_one}, detailed_output=True, retraw=True, **kw)
+    accumulated_visibility = torch.cumsum(det["fine_visibility_weights"], dim=-1)
+    median_indices = torch.min(torch.abs(accumulated_visibility - 0.5), dim=-1)[1]
+    surface = det["fine_input_pts"].numpy().reshape(n, -1, 3)[np.arange(n), median_indices.numpy(), :]
+    rigidity = det["fine_rigidity_mask"].numpy().reshape(n, -1)[np.arange(n), median_indices.numpy()]
+    np.savez_compressed(os.path.join(outdir, "caseJ_surface.npz"), seed=seed, n=n, rgb_map=np32(rgb), median_indices=median_indices.numpy(),
+                        surface_pts=surface.astype(np.float32), surface_rigidity=rigidity.astype(np.float32),
+                        fine_visibility_weights=np32(det["fine_visibility_weights"]))
     print("golden vectors written to", outdir)
 
 

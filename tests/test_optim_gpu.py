@@ -35,8 +35,47 @@ def test_matches_torch_adam_including_skipped_tensors_and_lr_changes():
     _lib.device_error_check()
     for a, b in zip(ours, ref):
         torch.testing.assert_close(a.detach(), b.detach(), rtol=2e-5, atol=1e-7)
-    sd = o1.state_dict()
-    assert int(sd["step"].max()) == 6 and int(sd["step"].min()) == 5 and sd["exp_avg"].shape == o1._flat.shape
+    # checkpoints interchange with torch.optim.Adam (train.py:682 loads, :1692 saves optimizer.state_dict())
+    sd, sd_ref = o1.state_dict(), o2.state_dict()
+    assert set(sd.keys()) == {"state", "param_groups"} and sd["param_groups"][0]["params"] == list(range(len(ours)))
+    steps = sorted(int(float(v["step"])) for v in sd["state"].values())
+    assert steps[0] == 5 and steps[-1] == 6
+    for i in sd_ref["state"]:
+        assert int(float(sd["state"][i]["step"])) == int(float(sd_ref["state"][i]["step"]))
+        torch.testing.assert_close(sd["state"][i]["exp_avg"], sd_ref["state"][i]["exp_avg"], rtol=2e-5, atol=1e-9)
+        torch.testing.assert_close(sd["state"][i]["exp_avg_sq"], sd_ref["state"][i]["exp_avg_sq"], rtol=2e-5, atol=1e-12)
+    # torch -> ours and ours -> torch, then one more identical step on both
+    o3 = optim.Adam([p.detach().clone().requires_grad_(True) for p in ref], lr=5e-4)
+    o3.load_state_dict(sd_ref)
+    o4 = torch.optim.Adam([p.detach().clone().requires_grad_(True) for p in ours], lr=5e-4)
+    o4.load_state_dict(sd)
+    gr = [torch.randn(p.shape, generator=g).to(DEV) for p in ours]
+    for opt in (o3, o4):
+        for p, gi in zip(opt.param_groups[0]["params"], gr):
+            p.grad = gi.clone()
+        opt.step()
+    for a, b in zip(o3.param_groups[0]["params"], o4.param_groups[0]["params"]):
+        torch.testing.assert_close(a.detach(), b.detach(), rtol=3e-5, atol=1e-7)
+
+
+def test_gradient_arena_zero_grad_and_in_place_accumulation():
+    from nonrigid_nerf_b200 import optim
+    ps = _make(5)
+    opt = optim.Adam(ps, lr=1e-3)
+    assert opt.grads_in_arena and all(p.grad is not None for p in ps)
+    arena = opt.gradient_arena()
+    (ps[5] ** 2).sum().backward()                    # ordinary autograd accumulates in place into the arena view
+    assert opt.grads_in_arena and float(arena.abs().sum()) > 0
+    torch.testing.assert_close(ps[5].grad, 2 * ps[5].detach())
+    opt.zero_grad(set_to_none=True)                  # keeps the views, one memset
+    assert opt.grads_in_arena and float(arena.abs().sum()) == 0
+    ps[3].grad = None                                # a caller may still re-bind: step() falls back to the pointer table
+    assert not opt.grads_in_arena
+    before = ps[3].detach().clone()
+    opt.step()
+    assert torch.equal(ps[3].detach(), before)
+    opt.zero_grad()
+    assert opt.grads_in_arena
 
 
 def test_training_trajectory_matches_torch_adam_and_refreshes_the_packed_weights():
