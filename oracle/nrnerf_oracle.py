@@ -198,7 +198,7 @@ def query_field(npar, bp, pts: Tensor, latents: Tensor, rigidity_cutoff=None, sc
 # --------------------------------------------------------------------------------------------
 def stratified_z(near: Tensor, far: Tensor, s: int, t_rand: Optional[Tensor], lindisp: bool = False) -> Tensor:
     """render_rays sampling part (train.py:847-869). near/far [N,1]."""
-    t = torch.linspace(0.0, 1.0, steps=s)
+    t = torch.linspace(0.0, 1.0, steps=s, device=near.device)
     if not lindisp:
         z = near * (1.0 - t) + far * t
     else:
@@ -251,8 +251,8 @@ def sample_pdf(bins: Tensor, weights: Tensor, u: Tensor) -> Tensor:
     return bin_b + t * (bin_a - bin_b)
 
 
-def det_u(n: int, n_imp: int) -> Tensor:
-    return torch.linspace(0.0, 1.0, steps=n_imp).expand(n, n_imp).contiguous()
+def det_u(n: int, n_imp: int, device=None) -> Tensor:
+    return torch.linspace(0.0, 1.0, steps=n_imp, device=device).expand(n, n_imp).contiguous()
 
 
 def render_rays(coarse, fine, bp, rays_o: Tensor, rays_d: Tensor, near, far, latents: Tensor,
@@ -262,8 +262,9 @@ def render_rays(coarse, fine, bp, rays_o: Tensor, rays_d: Tensor, near, far, lat
     """render_rays (train.py:792-980) with the coarse / importance-sample / fine assembly; keys as
     in the reference's result dict."""
     n = rays_o.shape[0]
-    near_t = torch.as_tensor(near, dtype=torch.float32).expand(n).reshape(n, 1)
-    far_t = torch.as_tensor(far, dtype=torch.float32).expand(n).reshape(n, 1)
+    # (device-agnostic: the training A/B of scripts/train_ab.py runs this restatement in fp32 on the GPU as the checker)
+    near_t = torch.as_tensor(near, dtype=torch.float32, device=rays_o.device).expand(n).reshape(n, 1)
+    far_t = torch.as_tensor(far, dtype=torch.float32, device=rays_o.device).expand(n).reshape(n, 1)
     z = stratified_z(near_t, far_t, s_c, rnd["t_rand"] if perturb else None, lindisp)
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
     raw, det_c = query_field(coarse, bp, pts, latents, rigidity_cutoff, scaling, removal_threshold)
@@ -273,7 +274,7 @@ def render_rays(coarse, fine, bp, rays_o: Tensor, rays_d: Tensor, near, far, lat
     if n_imp > 0:
         rgb0, disp0, acc0, alpha0, w0 = rgb, disp, acc, alpha, w
         z_mid = 0.5 * (z[:, 1:] + z[:, :-1])
-        u = rnd["u"] if perturb else det_u(n, n_imp)
+        u = rnd["u"] if perturb else det_u(n, n_imp, rays_o.device)
         z_samples = sample_pdf(z_mid, w[:, 1:-1], u).detach()
         z_f, _ = torch.sort(torch.cat([z, z_samples], -1), -1)
         pts_f = rays_o[:, None, :] + rays_d[:, None, :] * z_f[:, :, None]
@@ -340,7 +341,7 @@ def training_wrapper_loss(cp, fp, bp, rays: Dict[str, Tensor], latent_table: Ten
     (:173-189), training-mode render, data terms, offsets / rigidity regulariser and divergence regulariser, both
     scaled by the increasing schedule (1/100)^(1 - global_step / N_iters) (:229, :281).  Returns (loss, ret)."""
     n = rays["rays_o"].shape[0]
-    i2t = torch.as_tensor(imageid_to_timestepid)
+    i2t = torch.as_tensor(imageid_to_timestepid, device=pixel_indices.device)
     lat = latent_table[i2t[pixel_indices[:, 0]], :]
     ret = render_rays(cp, fp, bp, rays["rays_o"], rays["rays_d"], rays["near"], rays["far"], lat, s_c, n_imp, perturb=True,
                       raw_noise_std=1.0, rnd=rnd)
