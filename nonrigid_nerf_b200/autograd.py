@@ -56,47 +56,11 @@ def _split_flat(flat: torch.Tensor, like):
     return out
 
 
-class _ParamGroupFn(torch.autograd.Function):
-    """Ties a list of parameters to ONE autograd edge.  Forward returns a shape-only token (4 bytes of storage,
-    expanded to the group's element count); backward receives the group's flat gradient and hands out per-parameter
-    views.  The ray bender is used three times per training step (coarse pass, fine pass, divergence term): with one
-    edge autograd sums three flat buffers (2 add kernels) instead of accumulating 15 tensors twice (30 kernels)."""
-
-    @staticmethod
-    def forward(ctx, *params):
-        ctx.shapes = [p.shape for p in params]
-        ctx.needs = [p.requires_grad for p in params]
-        ctx.set_materialize_grads(False)
-        return params[0].new_empty(1).expand(sum(p.numel() for p in params))
-
-    @staticmethod
-    def backward(ctx, flat):
-        if flat is None:     # every user of the group wrote its gradient straight into the parameters' .grad arena
-            return (None,) * len(ctx.shapes)
-        out, o = [], 0
-        for shp, need in zip(ctx.shapes, ctx.needs):
-            n = 1
-            for d in shp:
-                n *= d
-            out.append(flat[o:o + n].view(shp) if need else None)
-            o += n
-        return tuple(out)
-
-
-def _bender_token(bender, bend_p) -> torch.Tensor:
-    """One token per bender and parameter state: every use of the bender inside one training step shares it."""
-    key = ops._versions(bend_p)
-    cache = getattr(bender, "_nrn_token", None)
-    if cache is not None and cache[0] == key:
-        return cache[1]
-    tok = _ParamGroupFn.apply(*bend_p)
-    bender._nrn_token = (key, tok)
-    return tok
-
-
 class _FieldTrainFn(torch.autograd.Function):
     """raw, unmasked_offsets, rigidity_mask (differentiable) + point details (not differentiable).
-    params = the NeRF's parameters in WGRAD order, followed (with a bender) by the bender's group token."""
+    params = the NeRF's parameters in WGRAD order, followed (with a bender) by the bender's parameters in WGRAD order.
+    (No autograd object outlives an iteration: a cached graph fragment would pin AccumulateGrad nodes -- and the CUDA
+    stream they were created on -- across iterations, which breaks CUDA-graph capture of the step.)"""
 
     @staticmethod
     def forward(ctx, net, rays, z_vals, latents, n_nerf, *params):
@@ -204,7 +168,11 @@ class _FieldTrainFn(torch.autograd.Function):
         else:
             grads = [g if p.requires_grad else None for g, p in zip(_split_flat(nerf_grad, nerf_p), nerf_p)]
         if bender is not None:
-            grads.append(None if bend_in_place else bend_grad)     # flat, for the bender's group token
+            bend_p = list(ctx.params[ctx.n_nerf:])
+            if bend_in_place:
+                grads += [None] * len(bend_p)
+            else:
+                grads += [g if p.requires_grad else None for g, p in zip(_split_flat(bend_grad, bend_p), bend_p)]
         return (None, None, None, d_lat, None, *grads)
 
 
@@ -298,7 +266,7 @@ class _DivergenceFn(torch.autograd.Function):
     """per-ray mean_s(w * (e^T J e)^2) of the offset field, closed-form forward and backward (csrc/div.cu)."""
 
     @staticmethod
-    def forward(ctx, unmasked, rigidity, weights, e, stash, bender, bender_token, w_is_alpha=False):
+    def forward(ctx, unmasked, rigidity, weights, e, stash, bender, w_is_alpha, *bend_p):
         n, s = unmasked.shape[0], unmasked.shape[1]
         dev = unmasked.device
         lib = _lib.load()
@@ -324,6 +292,7 @@ class _DivergenceFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.nrn_divergence_forward(C.byref(a)), "divergence_forward")
         ctx.keep = (un, rg, w, e, stash, tan, scal, bender)
+        ctx.bend_p = bend_p
         ctx.w_is_alpha = bool(w_is_alpha)
         ctx.shape = (n, s)
         ctx.in_shapes = (unmasked.shape, rigidity.shape)
@@ -365,7 +334,12 @@ class _DivergenceFn(torch.autograd.Function):
         a.stream = torch.cuda.current_stream().cuda_stream
         with torch.cuda.device(dev):
             _lib.check(lib.nrn_divergence_backward(C.byref(a)), "divergence_backward")
-        return (d_un.view(ctx.in_shapes[0]), d_rg.view(ctx.in_shapes[1]), None, None, None, None, bend_grad, None)
+        bend_p = list(ctx.bend_p)
+        if bend_grad is None:
+            pgrads = [None] * len(bend_p)
+        else:
+            pgrads = [g if p.requires_grad else None for g, p in zip(_split_flat(bend_grad, bend_p), bend_p)]
+        return (d_un.view(ctx.in_shapes[0]), d_rg.view(ctx.in_shapes[1]), None, None, None, None, None, *pgrads)
 
 
 def divergence_loss(unmasked: torch.Tensor, rigidity: torch.Tensor, weights: Optional[torch.Tensor], bender,
@@ -385,8 +359,8 @@ def divergence_loss(unmasked: torch.Tensor, rigidity: torch.Tensor, weights: Opt
         e = torch.randn(n * s, 3, device=unmasked.device)
     _, bend_p = _flat_params_bender(bender)
     if opacity_alpha is not None:
-        return _DivergenceFn.apply(unmasked, rigidity, opacity_alpha, e, stash, bender, _bender_token(bender, bend_p), True)
-    return _DivergenceFn.apply(unmasked, rigidity, weights, e, stash, bender, _bender_token(bender, bend_p), False)
+        return _DivergenceFn.apply(unmasked, rigidity, opacity_alpha, e, stash, bender, True, *bend_p)
+    return _DivergenceFn.apply(unmasked, rigidity, weights, e, stash, bender, False, *bend_p)
 
 
 def _flat_params_bender(bender):
@@ -511,8 +485,7 @@ def field(net, rays: torch.Tensor, z_vals: torch.Tensor, latents: Optional[torch
     if not _needs_grad(net, latents):
         return field_rays(net, rays, z_vals, latents, want_details)
     nerf_p, bend_p = _flat_params(net, bender)
-    tok = (_bender_token(bender, bend_p),) if bender is not None else ()
-    outs = _FieldTrainFn.apply(net, rays, z_vals, latents, len(nerf_p), *nerf_p, *tok)
+    outs = _FieldTrainFn.apply(net, rays, z_vals, latents, len(nerf_p), *nerf_p, *bend_p)
     if bender is not None:
         raw, un, rig, init, bent, masked = outs
         details = {"initial_input_pts": init, "unmasked_offsets": un, "rigidity_mask": rig, "masked_offsets": masked,

@@ -17,6 +17,7 @@
 namespace nrn {
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 cudaError_t launch_field_fwd2(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
+cudaError_t launch_field_fwd3(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 }
 
@@ -39,7 +40,7 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
   int* err_word = nullptr;   // [0] error word, [1] loss-scale source (float) of the running backward
   int num_sms = 0;
-  bool pair = true;
+  int fwd_kind = 1;          // 1 field_fwd.cu, 2 field_fwd2.cu (CTA pair), 3 field_fwd3.cu (shared-slab schedule)
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -58,8 +59,9 @@ int device_state(DeviceState** out) {
     if (const char* g = getenv("NRN_GRID")) { const int v = atoi(g); if (v > 0 && v < s.num_sms) s.num_sms = v; }   // developer experiments
     // forward field kernel: single-CTA kernel (field_fwd.cu) by default; NRN_PAIR=1 selects the CTA-pair kernel
     // (field_fwd2.cu, tcgen05 cta_group::2), which measures within +-5% of it
-    s.pair = false;
-    if (const char* g = getenv("NRN_PAIR")) s.pair = atoi(g) != 0;
+    s.fwd_kind = 1;
+    if (const char* g = getenv("NRN_PAIR")) s.fwd_kind = atoi(g) != 0 ? 2 : 1;
+    if (const char* g = getenv("NRN_FWD")) { const int v = atoi(g); if (v >= 1 && v <= 3) s.fwd_kind = v; }
     e = cudaMalloc(&s.err_word, 4 * sizeof(int));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(err word)");
     e = cudaMemset(s.err_word, 0, 4 * sizeof(int));
@@ -164,6 +166,15 @@ int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "sample_coarse_kernel");
 }
 
+int nrn_select_forward_kernel(int kind) {
+  if (kind < 1 || kind > 3) return fail(NRN_E_INVALID, "nrn_select_forward_kernel: kind %d (1 = two independent slots, 2 = CTA pair, 3 = shared-slab schedule)", kind);
+  DeviceState* ds;
+  const int rc = device_state(&ds);
+  if (rc) return rc;
+  ds->fwd_kind = kind;
+  return NRN_OK;
+}
+
 int nrn_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, float* rays_d, void* stream) {
   if (H < 0 || W < 0) return fail(NRN_E_INVALID, "nrn_get_rays: bad sizes");
   if (H == 0 || W == 0) return NRN_OK;
@@ -231,8 +242,14 @@ int nrn_field_forward(const NrnFieldArgs* a) {
   { const char* dm = getenv("NRN_DEBUG_MODE"); p.debug_mode = dm ? atoi(dm) : 0; }
   if (a->stash && a->points) return fail(NRN_E_INVALID, "nrn_field_forward: the training stash needs ray mode");
   p.err = ds->err_word;
-  cudaError_t e; { ScopedTimer tm(0, static_cast<cudaStream_t>(a->stream)); e = ds->pair ? nrn::launch_field_fwd2(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream))
-                 : nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream)); }
+  cudaError_t e;
+  {
+    ScopedTimer tm(0, static_cast<cudaStream_t>(a->stream));
+    const bool bend = a->bender_packed != nullptr;
+    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
+    e = ds->fwd_kind == 3 ? nrn::launch_field_fwd3(p, bend, ds->num_sms, st)
+        : ds->fwd_kind == 2 ? nrn::launch_field_fwd2(p, bend, ds->num_sms, st) : nrn::launch_field_fwd(p, bend, ds->num_sms, st);
+  }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "field_fwd_kernel");
 }
 

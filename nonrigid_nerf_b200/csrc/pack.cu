@@ -163,13 +163,49 @@ __device__ __forceinline__ void pack_bender_t_elem(const int idx, const BenderSr
 }
 
 
+// ---- split-order forward image (field_fwd3.cu): (layer, output half, K piece of 64) -> [8 chunks][128 rows][8] ----
+__device__ __forceinline__ void pack_nerf_split_elem(const int idx, const NerfSrc& src, int in_ch, int out_ch, __half* __restrict__ w) {
+  if (idx >= kNerfWBytes / 2) return;
+  constexpr int piece = 8 * 128 * 8;          // elements per piece
+  constexpr int n_main = (2 + 6 * 8 + 10) * piece;
+  float v = 0.f;
+  if (idx < n_main) {
+    int pi = idx / piece;                      // piece index in streaming order
+    const int rem = idx - pi * piece;
+    const int c = rem / (128 * 8), r = (rem >> 3) & 127, e = rem & 7;
+    int L = 0;
+    for (;; ++L) {
+      const int np = L == 0 ? 2 : (L == 5 ? 10 : 8);
+      if (pi < np) break;
+      pi -= np;
+    }
+    const int nk = L == 0 ? 1 : (L == 5 ? 5 : 4);
+    const int nh = pi / nk, ks = pi - nh * nk;
+    const int row = nh * 128 + r;
+    const int k = ks * 64 + c * 8 + e;         // column inside the layer's padded K
+    if (L == 0) v = k < in_ch ? src.w[0][row * in_ch + k] : 0.f;
+    else if (L == 5) {
+      const int ld = in_ch + 256;
+      if (k < 64) v = k < in_ch ? src.w[5][row * ld + k] : 0.f;
+      else v = src.w[5][row * ld + in_ch + (k - 64)];
+    } else v = src.w[L][row * 256 + k];
+  } else {                                     // head, N padded to 16
+    int k, r;
+    decode(idx - n_main, 16, k, r);
+    v = r < out_ch ? src.w[8][r * 256 + k] : 0.f;
+  }
+  w[idx] = __float2half_rn(v);
+}
+
 // one launch per module: the first blocks write the forward images (+ biases), the rest the transposed images
 constexpr int kPackThreads = 256;
 __global__ void __launch_bounds__(kPackThreads) pack_nerf_kernel(NerfSrc src, int in_ch, int out_ch, __half* __restrict__ w,
-                                                                 float* __restrict__ bias, __half* __restrict__ wt) {
+                                                                 float* __restrict__ bias, __half* __restrict__ wt, __half* __restrict__ ws) {
   constexpr int nb_fwd = (kNerfWBytes / 2 + kPackThreads - 1) / kPackThreads;
+  constexpr int nb_t = (kNerfTWBytes / 2 + kPackThreads - 1) / kPackThreads;
   if (blockIdx.x < nb_fwd) pack_nerf_elem(blockIdx.x * kPackThreads + threadIdx.x, src, in_ch, out_ch, w, bias);
-  else pack_nerf_t_elem((blockIdx.x - nb_fwd) * kPackThreads + threadIdx.x, src, in_ch, out_ch, wt);
+  else if (blockIdx.x < nb_fwd + nb_t) pack_nerf_t_elem((blockIdx.x - nb_fwd) * kPackThreads + threadIdx.x, src, in_ch, out_ch, wt);
+  else pack_nerf_split_elem((blockIdx.x - nb_fwd - nb_t) * kPackThreads + threadIdx.x, src, in_ch, out_ch, ws);
 }
 __global__ void __launch_bounds__(kPackThreads) pack_bender_kernel(BenderSrc src, __half* __restrict__ w, float* __restrict__ bias,
                                                                    __half* __restrict__ wt) {
@@ -183,9 +219,10 @@ __global__ void __launch_bounds__(kPackThreads) pack_bender_kernel(BenderSrc src
 // packed = [forward images | biases | transposed images] (offsets in nrn_common.cuh)
 cudaError_t launch_pack_nerf(const NerfSrc& src, int in_ch, int out_ch, void* packed, cudaStream_t st) {
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
-  const int nb = (kNerfWBytes / 2 + kPackThreads - 1) / kPackThreads + (kNerfTWBytes / 2 + kPackThreads - 1) / kPackThreads;
+  const int nb = 2 * ((kNerfWBytes / 2 + kPackThreads - 1) / kPackThreads) + (kNerfTWBytes / 2 + kPackThreads - 1) / kPackThreads;
   pack_nerf_kernel<<<nb, kPackThreads, 0, st>>>(src, in_ch, out_ch, reinterpret_cast<__half*>(base),
-                                               reinterpret_cast<float*>(base + kNerfWBytes), reinterpret_cast<__half*>(base + kNerfTOffset));
+                                               reinterpret_cast<float*>(base + kNerfWBytes), reinterpret_cast<__half*>(base + kNerfTOffset),
+                                               reinterpret_cast<__half*>(base + kNerfSOffset));
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bender(const BenderSrc& src, void* packed, cudaStream_t st) {

@@ -174,3 +174,41 @@ torch.save(out, sys.argv[1])
     assert outs[0].keys() == outs[1].keys() and len(outs[0]) == 4
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_shared_slab_forward_kernel_is_bit_identical_incl_training_stash():
+    """field_fwd3.cu (one weight stream per CTA shared by both tile slots, half-layer pipelining) performs the same MMAs in
+    the same K order and the same epilogue arithmetic as field_fwd.cu: raw output, point details and every byte of the
+    training stash must be equal -- inference and training mode, with / without bender, ragged and multi-wave sizes."""
+    from nonrigid_nerf_b200 import autograd as ag, ops, _lib
+    dev = _dev()
+    lib = _lib.load()
+    coarse, fine, bender, _ = helpers.build_models(O, 19, dev, True)
+    try:
+        for n, s in ((37, 64), (300, 128), (2500, 64), (5, 3)):
+            r = O.make_rays(19, n)
+            rays = helpers.rays8(r, dev)
+            z = ops.sample_coarse(rays, s, None, False)
+            for with_b in (True, False):
+                coarse.ray_bender = (bender if with_b else None,)
+                lat = r["latents"].to(dev) if with_b else None
+                got = {}
+                for kind in (1, 3):
+                    _lib.check(lib.nrn_select_forward_kernel(kind), "select")
+                    raw, det = ag.field_rays(coarse, rays, z, lat, True)
+                    stash = torch.zeros(lib.nrn_stash_bytes(n, s), dtype=torch.uint8, device=dev)
+                    nerf_pack = ops.pack_nerf(coarse)
+                    bender_pack = ops.pack_bender(bender) if with_b else None
+                    raw_t, det_t = ops.field_forward(rays, z, lat, nerf_pack, bender_pack, 5, None, None, None, True, stash)
+                    _lib.device_error_check()
+                    got[kind] = (raw, det, raw_t, det_t, stash)
+                a, b = got[1], got[3]
+                assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[0], a[2]), (n, s, with_b)
+                for k in a[1]:
+                    assert torch.equal(a[1][k], b[1][k]) and torch.equal(a[3][k], b[3][k]), (n, s, with_b, k)
+                n_tiles = (n * s + 127) // 128
+                used = n_tiles * 634880
+                assert torch.equal(a[4][:used], b[4][:used]), (n, s, with_b, "stash")
+    finally:
+        coarse.ray_bender = (bender,)
+        lib.nrn_select_forward_kernel(1)

@@ -103,7 +103,7 @@ def test_training_wrapper_loss_and_gradients_match_executed_reference():
         e_lat = _rel(lg, torch.from_numpy(g["latent_grads"]))
         print(f"[arena={use_arena}] worst sampled gradient error {worst:.3e}; latent table gradient {e_lat:.3e}")
         assert e_lat <= 8e-2, e_lat
-        results[use_arena] = [p.grad.detach().clone() for _, p in named] + [lg]
+        results[use_arena] = [None if p.grad is None else p.grad.detach().clone() for _, p in named] + [lg]
         if use_arena:
             assert coarse.views_linears[0].weight.grad.abs().max() == 0   # dead weight: zero gradient in the arena
         else:
@@ -192,7 +192,7 @@ def test_point_mode_entries_run_network_and_nerf_forward():
     assert torch.equal(out.reshape(-1, 5), raw2)
     np.testing.assert_allclose(det["unmasked_offsets"].reshape(-1, 3).cpu().numpy(), ref_det["unmasked_offsets"].numpy(), atol=1e-4)
     np.testing.assert_allclose(det["rigidity_mask"].reshape(-1).cpu().numpy(), ref_det["rigidity_mask"].reshape(-1).numpy(), atol=3e-4)
-    np.testing.assert_allclose(det2["input_pts"].cpu().numpy(), ref_det["input_pts"].numpy(), atol=2e-5)
+    np.testing.assert_allclose(det2["input_pts"].cpu().numpy(), ref_det["input_pts"].numpy(), atol=1e-4)
     with pytest.raises(RuntimeError):
         coarse(x.to(DEV).requires_grad_(True))   # the point-wise entry is inference-only: differentiable use fails loudly
 
