@@ -480,7 +480,8 @@ Schedule build_schedule(bool has_bender) {
         else { a_off = ks * 8 * kChunkBytes; kh = ks / 2; }
         if (nh == 0) {
           if (L == 0) w0 = ks == 0;                                   // positional encoding written
-          else if (L == 5) { w0 = ks == 1; w1 = ks == 3; }           // (the embedding piece needs nothing new)
+          else if (L == 5) { w0 = ks == 0; w1 = ks == 3; }           // the embedding piece reads nothing new, but it OVERWRITES
+                                                                     // accumulator half 0: L4's half-0 epilogue must have drained it
           else { w0 = ks == 0; w1 = ks == 2; }
         }
         int commit = COMMIT_NONE;
