@@ -51,6 +51,8 @@ int nrn_pack_bender(const float* const* net_w /*5*/, const float* const* net_b /
  * 1 = two independent tile slots per CTA (field_fwd.cu), 2 = CTA pair / cta_group::2 (field_fwd2.cu), 3 = shared-slab
  * schedule with half-layer pipelining (field_fwd3.cu).  The default can also be set with the environment variable NRN_FWD. */
 int nrn_select_forward_kernel(int kind);
+/* Likewise for the DGRAD kernel nrn_field_backward launches: 1 = field_bwd.cu, 3 = field_bwd3.cu (environment: NRN_BWD). */
+int nrn_select_backward_kernel(int kind);
 
 /* ---- ray generation: get_rays / get_rays_np (run_nerf_helpers.py:588-622) on the device -----------------------------
  * c2w [3][4] row-major, intrinsics = (focal_x, focal_y, center_x, center_y); rays_o / rays_d [H*W][3] in the [H, W, 3]

@@ -19,6 +19,7 @@ cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_s
 cudaError_t launch_field_fwd2(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 cudaError_t launch_field_fwd3(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
+cudaError_t launch_field_bwd3(const FieldBwdParams& p, const uint8_t* nerf_packed_base, bool has_bender, int num_sms, cudaStream_t stream);
 }
 
 namespace {
@@ -41,6 +42,7 @@ struct DeviceState {
   int* err_word = nullptr;   // [0] error word, [1] loss-scale source (float) of the running backward
   int num_sms = 0;
   int fwd_kind = 1;          // 1 field_fwd.cu, 2 field_fwd2.cu (CTA pair), 3 field_fwd3.cu (shared-slab schedule)
+  int bwd_kind = 1;          // 1 field_bwd.cu, 3 field_bwd3.cu (shared-slab schedule)
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -62,6 +64,8 @@ int device_state(DeviceState** out) {
     s.fwd_kind = 1;
     if (const char* g = getenv("NRN_PAIR")) s.fwd_kind = atoi(g) != 0 ? 2 : 1;
     if (const char* g = getenv("NRN_FWD")) { const int v = atoi(g); if (v >= 1 && v <= 3) s.fwd_kind = v; }
+    s.bwd_kind = 1;
+    if (const char* g = getenv("NRN_BWD")) { const int v = atoi(g); if (v == 1 || v == 3) s.bwd_kind = v; }
     e = cudaMalloc(&s.err_word, 4 * sizeof(int));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(err word)");
     e = cudaMemset(s.err_word, 0, 4 * sizeof(int));
@@ -172,6 +176,15 @@ int nrn_select_forward_kernel(int kind) {
   const int rc = device_state(&ds);
   if (rc) return rc;
   ds->fwd_kind = kind;
+  return NRN_OK;
+}
+
+int nrn_select_backward_kernel(int kind) {
+  if (kind != 1 && kind != 3) return fail(NRN_E_INVALID, "nrn_select_backward_kernel: kind %d (1 = two independent slots, 3 = shared-slab schedule)", kind);
+  DeviceState* ds;
+  const int rc = device_state(&ds);
+  if (rc) return rc;
+  ds->bwd_kind = kind;
   return NRN_OK;
 }
 
@@ -353,7 +366,11 @@ int nrn_field_backward(const NrnFieldBwdArgs* a) {
   if (e == cudaSuccess && bend && p.d_unmasked_up) e = nrn::launch_absmax(p.d_unmasked_up, p.P * 3, amax, st, true);
   if (e == cudaSuccess && bend && p.d_rigid_up) e = nrn::launch_absmax(p.d_rigid_up, p.P, amax, st, true);
   if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
-  { ScopedTimer tm(1, st); e = nrn::launch_field_bwd(p, bend, ds->num_sms, st); }
+  {
+    ScopedTimer tm(1, st);
+    e = ds->bwd_kind == 3 ? nrn::launch_field_bwd3(p, static_cast<const uint8_t*>(a->nerf_packed), bend, ds->num_sms, st)
+                          : nrn::launch_field_bwd(p, bend, ds->num_sms, st);
+  }
   if (e != cudaSuccess) return cuda_fail(e, "field_bwd_kernel");
   nrn::WgradParams w{};
   w.stash = p.stash; w.gstash = p.gstash; w.scratch = a->wgrad_scratch; w.amax = amax; w.n_tiles = p.n_tiles; w.err = ds->err_word;

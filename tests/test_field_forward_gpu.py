@@ -212,3 +212,61 @@ def test_shared_slab_forward_kernel_is_bit_identical_incl_training_stash():
     finally:
         coarse.ray_bender = (bender,)
         lib.nrn_select_forward_kernel(1)
+
+
+def test_shared_slab_dgrad_kernel_is_bit_identical_incl_gradient_stash():
+    """field_bwd3.cu vs field_bwd.cu through nrn_field_backward: the gradient stash (every dY image), hence the weight
+    gradients WGRAD derives from it, must be equal bit for bit; the per-ray latent gradient is accumulated with fp32 atomics
+    in both kernels (order-dependent): equal to rounding."""
+    import ctypes as C
+    from nonrigid_nerf_b200 import ops, _lib
+    dev = _dev()
+    lib = _lib.load()
+    coarse, fine, bender, _ = helpers.build_models(O, 23, dev, True)
+    try:
+        for n, s, with_b in ((37, 64, True), (700, 128, True), (2500, 64, True), (2500, 64, False), (5, 3, True)):
+            r = O.make_rays(23, n)
+            rays = helpers.rays8(r, dev)
+            z = ops.sample_coarse(rays, s, None, False)
+            lat = r["latents"].to(dev) if with_b else None
+            nerf_pack = ops.pack_nerf(coarse)
+            bender_pack = ops.pack_bender(bender) if with_b else None
+            stash = torch.zeros(lib.nrn_stash_bytes(n, s), dtype=torch.uint8, device=dev)
+            raw, det = ops.field_forward(rays, z, lat, nerf_pack, bender_pack, 5, None, None, None, True, stash)
+            g = torch.Generator().manual_seed(n)
+            d_raw = (torch.randn(n, s, 5, generator=g) * 1e-3).to(dev)
+            d_un = (torch.randn(n * s, 3, generator=g) * 1e-2).to(dev)
+            d_rg = (torch.randn(n * s, generator=g) * 1e-3).to(dev)
+            got = {}
+            for kind in (1, 3):
+                _lib.check(lib.nrn_select_backward_kernel(kind), "select")
+                a = _lib.NrnFieldBwdArgs()
+                a.n_rays, a.n_samples, a.out_ch = n, s, 5
+                a.d_raw, a.stash = d_raw.data_ptr(), stash.data_ptr()
+                gstash = torch.zeros(lib.nrn_grad_stash_bytes(n, s), dtype=torch.uint8, device=dev)
+                scratch = torch.empty(lib.nrn_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
+                a.grad_stash, a.wgrad_scratch = gstash.data_ptr(), scratch.data_ptr()
+                a.nerf_packed = nerf_pack.data_ptr()
+                nerf_grad = torch.empty(lib.nrn_nerf_grad_floats(5), dtype=torch.float32, device=dev)
+                a.nerf_grad = nerf_grad.data_ptr()
+                bend_grad = d_lat = None
+                if with_b:
+                    a.bender_packed = bender_pack.data_ptr()
+                    a.unmasked_offsets, a.rigidity_mask = det["unmasked_offsets"].data_ptr(), det["rigidity_mask"].data_ptr()
+                    a.d_unmasked_offsets, a.d_rigidity_mask = d_un.data_ptr(), d_rg.data_ptr()
+                    bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
+                    d_lat = torch.empty(n, 32, dtype=torch.float32, device=dev)
+                    a.bender_grad, a.d_latents = bend_grad.data_ptr(), d_lat.data_ptr()
+                a.stream = torch.cuda.current_stream().cuda_stream
+                _lib.check(lib.nrn_field_backward(C.byref(a)), "field_backward")
+                _lib.device_error_check()
+                got[kind] = (gstash, nerf_grad, bend_grad, d_lat)
+            n_tiles = (n * s + 127) // 128
+            used = n_tiles * 618496
+            assert torch.equal(got[1][0][:used], got[3][0][:used]), (n, s, with_b, "gradient stash")
+            assert torch.equal(got[1][1], got[3][1]), (n, s, with_b, "nerf grad")
+            if with_b:
+                assert torch.equal(got[1][2], got[3][2]), (n, s, with_b, "bender grad")
+                torch.testing.assert_close(got[3][3], got[1][3], rtol=1e-4, atol=1e-9)
+    finally:
+        lib.nrn_select_backward_kernel(1)
