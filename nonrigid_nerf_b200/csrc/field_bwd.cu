@@ -24,9 +24,7 @@ namespace nrn {
 namespace {
 
 constexpr long long kWaitLimitCycles = 1ll << 28;
-// weight stream in pieces of at most 16 KB through a 6-stage ring (see field_fwd.cu: deeper ring, more loads in flight)
-constexpr int kBwdRingStages = 6;
-constexpr uint32_t kBwdPieceBytes = 16384;
+constexpr int kBwdRingStages = 3;
 
 struct Shared {
   uint64_t w_full[kBwdRingStages];
@@ -38,24 +36,22 @@ struct Shared {
 };
 
 struct StepShape {
-  uint32_t N, nslabs, slab_bytes, k16, a_chunks;   // a_chunks: A-operand chunks (K / 8) one piece advances
+  uint32_t N, nslabs, slab_bytes, k16;
 };
 
 __device__ __forceinline__ StepShape step_shape(int step) {
   switch (step) {
-    case 0: return {256u, 1u, (uint32_t)kNerfTHeadBytes, 1u, 2u};
-    case 3: return {64u, 2u, kBwdPieceBytes, 8u, 16u};
-    case 9: return {64u, 2u, kBwdPieceBytes, 8u, 16u};
-    case 10: return {64u, 1u, (uint32_t)kBendTB4Bytes, 1u, 2u};
-    case 11: return {64u, 1u, (uint32_t)kBendTB3Bytes, 4u, 8u};
-    case 12: return {96u, 1u, (uint32_t)kBendTB2Bytes, 5u, 10u};
-    case 13: return {96u, 2u, 8u * 96u * 16u, 4u, 8u};       // K = 96 as 64 + 32 (second piece: 4 chunks, k16 = 2)
-    case 14: return {48u, 1u, (uint32_t)kBendTB0Bytes, 6u, 12u};
-    default: return {256u, 8u, kBwdPieceBytes, 2u, 4u};
+    case 0: return {256u, 1u, (uint32_t)kNerfTHeadBytes, 1u};
+    case 3: return {64u, 1u, 32768u, 16u};
+    case 9: return {64u, 1u, 32768u, 16u};
+    case 10: return {64u, 1u, (uint32_t)kBendTB4Bytes, 1u};
+    case 11: return {64u, 1u, (uint32_t)kBendTB3Bytes, 4u};
+    case 12: return {96u, 1u, (uint32_t)kBendTB2Bytes, 5u};
+    case 13: return {96u, 1u, (uint32_t)kBendTB1Bytes, 6u};
+    case 14: return {48u, 1u, (uint32_t)kBendTB0Bytes, 6u};
+    default: return {256u, 4u, 32768u, 4u};
   }
 }
-__device__ __forceinline__ uint32_t piece_bytes(int step, const StepShape& s, uint32_t j) { return (step == 13 && j == 1) ? 4u * 96u * 16u : s.slab_bytes; }
-__device__ __forceinline__ uint32_t piece_k16(int step, const StepShape& s, uint32_t j) { return (step == 13 && j == 1) ? 2u : s.k16; }
 
 struct Waiter {
   int* s_abort;
@@ -172,7 +168,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                       // 2 slots x 64 KB gradient operand
   uint8_t* ring = smem + 2 * kHBytes;        // kBwdRingStages x 32 KB
-  Shared* sh = reinterpret_cast<Shared*>(ring + kBwdRingStages * kBwdPieceBytes);
+  Shared* sh = reinterpret_cast<Shared*>(ring + kBwdRingStages * kRingStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -212,17 +208,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
           const StepShape s = step_shape(step);
           const uint8_t* src = step < 10 ? p.nerf_wT + gn : p.bend_wT + gb;
           for (int slot = 0; slot < 2; ++slot) {
-            uint32_t off = 0;
             for (uint32_t j = 0; j < s.nslabs; ++j) {
-              const uint32_t bytes = piece_bytes(step, s, j);
               W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
-              mbar_arrive_expect_tx(&sh->w_full[stage], bytes);
-              tma_bulk_g2s(ring + stage * kBwdPieceBytes, src + off, bytes, &sh->w_full[stage]);
-              off += bytes;
+              uint8_t* dst = ring + stage * kRingStageBytes;
+              mbar_arrive_expect_tx(&sh->w_full[stage], s.slab_bytes);
+              const uint8_t* g = src + j * s.slab_bytes;
+              for (uint32_t off = 0; off < s.slab_bytes; off += 16384u) {
+                const uint32_t n = s.slab_bytes - off < 16384u ? s.slab_bytes - off : 16384u;
+                tma_bulk_g2s(dst + off, g + off, n, &sh->w_full[stage]);
+              }
               if (++stage == kBwdRingStages) { stage = 0; phase ^= 1u; }
             }
           }
-          { uint32_t tot = 0; for (uint32_t j = 0; j < s.nslabs; ++j) tot += piece_bytes(step, s, j); if (step < 10) gn += tot; else gb += tot; }
+          if (step < 10) gn += s.nslabs * s.slab_bytes; else gb += s.nslabs * s.slab_bytes;
         }
       }
     }
@@ -245,10 +243,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
             for (uint32_t j = 0; j < s.nslabs; ++j) {
               W.wait(&sh->w_full[stage], phase, 202);
               tc_fence_after_sync();
-              const uint64_t adesc = umma_smem_desc(a_base + j * s.a_chunks * kChunkBytes, kChunkBytes, 128);
-              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kBwdPieceBytes), s.N * 16, 128);
-              const uint32_t k16 = piece_k16(step, s, j);
-              for (uint32_t k = 0; k < k16; ++k) {
+              const uint64_t adesc = umma_smem_desc(a_base + j * 8 * kChunkBytes, kChunkBytes, 128);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
+              for (uint32_t k = 0; k < s.k16; ++k) {
                 umma_f16_ss(d_tmem, umma_desc_advance(adesc, k * 2 * kChunkBytes),
                             umma_desc_advance(bdesc, k * 2 * s.N * 16), idesc, (j | k) ? 1u : 0u);
               }
@@ -470,7 +467,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_bwd_kernel(const FieldBw
 
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, int num_sms, cudaStream_t stream) {
-  const size_t smem = 2 * kHBytes + kBwdRingStages * kBwdPieceBytes + sizeof(Shared) + 64;
+  const size_t smem = 2 * kHBytes + kBwdRingStages * kRingStageBytes + sizeof(Shared) + 64;
   const int n_pairs = (p.n_tiles + 1) / 2;
   if (n_pairs <= 0) return cudaSuccess;
   const int grid = n_pairs < num_sms ? n_pairs : num_sms;

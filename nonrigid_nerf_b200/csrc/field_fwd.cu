@@ -29,8 +29,8 @@ namespace {
 constexpr long long kWaitLimitCycles = 1ll << 28;  // ~0.14 s: protocol bug => error flag, not a hang
 
 struct Shared {
-  uint64_t w_full[4];
-  uint64_t w_empty[4];
+  uint64_t w_full[kRingStages];
+  uint64_t w_empty[kRingStages];
   uint64_t a_ready[2];
   uint64_t d_full[2];
   uint32_t tmem_base;
@@ -41,36 +41,26 @@ struct StepShape {
   uint32_t N, nslabs, slab_bytes, k16;
 };
 
-// The weight stream moves in pieces of at most kPieceBytes (16 KB): a deeper ring (4 stages instead of 2 x 32 KB) keeps three
-// loads in flight while one piece is consumed -- with 32 KB slabs only one load was ever outstanding and every slab cost a full
-// L2 round trip (~0.5 us), which made the MMA block of a layer 2.2 us instead of the 1.04 us the tensor pipe needs.
-constexpr uint32_t kPieceBytes = 16384;
-constexpr int kPieceStages = 4;
-
-// step index: 0-4 bender B0..B4, 5-12 NeRF L0..L7, 13 head.  A 256-row image advances K by 32 per 16 KB piece.
+// step index: 0-4 bender B0..B4, 5-12 NeRF L0..L7, 13 head
 __device__ __forceinline__ StepShape step_shape(int step) {
   switch (step) {
     case 0: return {96u, 1u, (uint32_t)kBendB0Bytes, 3u};
-    case 1: return {96u, 2u, 8u * 96u * 16u, 4u};          // K = 96 as 64 + 32: second piece 4 chunks, k16 = 2 (see piece_*)
+    case 1: return {96u, 1u, (uint32_t)kBendB1Bytes, 6u};
     case 2: return {80u, 1u, (uint32_t)kBendB2Bytes, 6u};
     case 3: return {64u, 1u, (uint32_t)kBendB3Bytes, 4u};
     case 4: return {16u, 1u, (uint32_t)kBendB4Bytes, 4u};
-    case 5: return {256u, 2u, kPieceBytes, 2u};
-    case 10: return {256u, 10u, kPieceBytes, 2u};
+    case 5: return {256u, 1u, 32768u, 4u};
+    case 10: return {256u, 5u, 32768u, 4u};
     case 13: return {16u, 1u, (uint32_t)kNerfHeadBytes, 16u};
-    default: return {256u, 8u, kPieceBytes, 2u};
+    default: return {256u, 4u, 32768u, 4u};
   }
 }
-__device__ __forceinline__ uint32_t piece_bytes(int step, const StepShape& s, uint32_t j) { return (step == 1 && j == 1) ? 4u * 96u * 16u : s.slab_bytes; }
-__device__ __forceinline__ uint32_t piece_k16(int step, const StepShape& s, uint32_t j) { return (step == 1 && j == 1) ? 2u : s.k16; }
-// byte offset (inside a slot's activation region: H at 0, E at kHBytes) of the A operand of piece j
+// byte offset (inside a slot's activation region: H at 0, E at kHBytes) of the A operand of slab j
 __device__ __forceinline__ uint32_t a_operand_offset(int step, uint32_t j) {
-  if (step == 0) return kHBytes;                                        // bender input lives in E
-  if (step == 1) return j * 8 * kChunkBytes;
-  if (step == 5) return kHBytes + j * 4 * kChunkBytes;                  // embedding, K = 32 per piece
-  if (step == 10) return j < 2 ? kHBytes + j * 4 * kChunkBytes : (j - 2) * 4 * kChunkBytes;  // skip: [embedding | h]
+  if (step == 0 || step == 5) return kHBytes;                       // bender input / embedding live in E
+  if (step == 10) return j == 0 ? kHBytes : (j - 1) * 8 * kChunkBytes;  // skip: [embedding | h]
   if (step < 5 || step == 13) return 0;
-  return j * 4 * kChunkBytes;
+  return j * 8 * kChunkBytes;
 }
 
 struct Waiter {
@@ -168,7 +158,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;                                  // 2 slots x (H | E)
   uint8_t* ring = smem + 2 * kSlotBytes;                // kRingStages x 32 KB
-  Shared* sh = reinterpret_cast<Shared*>(ring + kPieceStages * kPieceBytes);
+  Shared* sh = reinterpret_cast<Shared*>(ring + kRingStages * kRingStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -176,7 +166,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
   constexpr int kFirstStep = HAS_BENDER ? 0 : 5;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kPieceStages; ++i) {
+    for (int i = 0; i < kRingStages; ++i) {
       mbar_init(&sh->w_full[i], 1);
       mbar_init(&sh->w_empty[i], 1);
     }
@@ -208,17 +198,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           const StepShape s = step_shape(step);
           const uint8_t* src = step < 5 ? p.bend_w + gb : p.nerf_w + gn;
           for (int slot = 0; slot < 2; ++slot) {
-            uint32_t off = 0;
             for (uint32_t j = 0; j < s.nslabs; ++j) {
-              const uint32_t bytes = piece_bytes(step, s, j);
               W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
-              mbar_arrive_expect_tx(&sh->w_full[stage], bytes);
-              tma_bulk_g2s(ring + stage * kPieceBytes, src + off, bytes, &sh->w_full[stage]);
-              off += bytes;
-              if (++stage == kPieceStages) { stage = 0; phase ^= 1u; }
+              uint8_t* dst = ring + stage * kRingStageBytes;
+              mbar_arrive_expect_tx(&sh->w_full[stage], s.slab_bytes);
+              const uint8_t* g = src + j * s.slab_bytes;
+              for (uint32_t off = 0; off < s.slab_bytes; off += 16384u) {
+                const uint32_t n = s.slab_bytes - off < 16384u ? s.slab_bytes - off : 16384u;
+                tma_bulk_g2s(dst + off, g + off, n, &sh->w_full[stage]);
+              }
+              if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
             }
           }
-          { uint32_t tot = 0; for (uint32_t j = 0; j < s.nslabs; ++j) tot += piece_bytes(step, s, j); if (step < 5) gb += tot; else gn += tot; }
+          if (step < 5) gb += s.nslabs * s.slab_bytes; else gn += s.nslabs * s.slab_bytes;
         }
       }
     }
@@ -242,14 +234,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
               W.wait(&sh->w_full[stage], phase, 202);
               tc_fence_after_sync();
               const uint64_t adesc = umma_smem_desc(a_base + a_operand_offset(step, j), kChunkBytes, 128);
-              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kPieceBytes), s.N * 16, 128);
-              const uint32_t k16 = piece_k16(step, s, j);
-              for (uint32_t k = 0; k < k16 && p.debug_mode != 2; ++k) {
+              const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
+              for (uint32_t k = 0; k < s.k16 && p.debug_mode != 2; ++k) {
                 umma_f16_ss(d_tmem, umma_desc_advance(adesc, k * 2 * kChunkBytes),
                             umma_desc_advance(bdesc, k * 2 * s.N * 16), idesc, (j | k) ? 1u : 0u);
               }
-              umma_commit(&sh->w_empty[stage]);  // piece free once these MMAs retire
-              if (++stage == kPieceStages) { stage = 0; phase ^= 1u; }
+              umma_commit(&sh->w_empty[stage]);  // slab free once these MMAs retire
+              if (++stage == kRingStages) { stage = 0; phase ^= 1u; }
             }
             umma_commit(&sh->d_full[slot]);      // accumulator complete
           }
@@ -444,7 +435,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t field_fwd_smem_bytes() { return 2 * kSlotBytes + kPieceStages * kPieceBytes + sizeof(Shared) + 64; }
+size_t field_fwd_smem_bytes() { return 2 * kSlotBytes + kRingStages * kRingStageBytes + sizeof(Shared) + 64; }
 
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream) {
   const size_t smem = field_fwd_smem_bytes();
