@@ -63,7 +63,11 @@ def run(args, rank, local_rank, world):
         rays_o, rays_d = rays_o_h.to(dev), rays_d_h.to(dev)
         lat_dev = latents_h.to(dev)
         results = {}
-        for detailed in (False, True):
+        d2h = {}
+        # three ways to get a frame: plain (rgb, disp), "surface" (+ the fused free-viewpoint post-processing: median-visibility
+        # sample's canonical point and rigidity, 4 floats + an index per ray), "detailed" (the reference's default in render_path:
+        # every per-sample tensor, which render_path then copies to the host, train.py:484-492)
+        for mode in ("plain", "surface", "detailed"):
             def frame(k, e2e):
                 with torch.no_grad():
                     if e2e:
@@ -72,38 +76,45 @@ def run(args, rank, local_rank, world):
                     else:
                         ro, rd, lat = rays_o, rays_d, lat_dev[k % 256]
                     rgb, disp, acc, extras = T.render(ro, rd, chunk=65536, additional_pixel_information={"ray_bending_latents": lat[None].expand(n, 32)},
-                                                      detailed_output=detailed, **kw)
+                                                      detailed_output=(mode == "detailed"), surface_output=(mode == "surface"), **kw)
                     if e2e:
-                        return rgb.cpu(), disp.cpu()      # what render_path keeps per frame (train.py:481-483)
+                        host = [rgb.cpu(), disp.cpu()]                     # what render_path keeps per frame (train.py:481-483)
+                        if mode != "plain":
+                            host += [v.cpu() for v in extras.values()]      # train.py:484-492 / the 4 floats per ray
+                        d2h[mode] = int(sum(t.numel() * t.element_size() for t in host))
+                        return host
                     return rgb
             for k in range(args.warmup):
                 frame(k, False)
             out = {}
+            n_e2e = args.steps if mode != "detailed" else max(2, args.steps // 5)   # 2.3 GB per frame over PCIe: a few frames suffice
             for e2e in (False, True):
+                reps = n_e2e if e2e else args.steps
                 sync_all()
                 e0, e1 = _events()
                 e0.record()
-                for k in range(args.steps):
+                for k in range(reps):
                     frame(k, e2e)
                 e1.record()
                 sync_all()
-                out[e2e] = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-            results[detailed] = out
+                out[e2e] = max_over_ranks(e0.elapsed_time(e1)) / reps
+            results[mode] = out
         _lib.device_error_check()
         if world > 1:
             dist.destroy_process_group()
         if rank != 0:
             return
-        ms = results[False][False]
+        ms = results["plain"][False]
         tf = n * bench.POINTS_PER_RAY * bench.FLOP_PER_POINT / (ms * 1e-3) / 1e12
         line = {"metric": "rays/sec (64c+128f samples, 8x256 MLP), full-frame test-time render", "value": world * n / (ms * 1e-3), "unit": "rays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 (tensor-core operands; f32 accumulate)", "data": "synthetic",
                 "config": {"workload": "free_viewpoint_rendering full-frame forward 504x378, fixed pose, one latent per frame, 64c+128f, det sampling, chunk=65536",
                            "parallelism": f"frames partitioned over {world} rank(s), no collective", "l2": "each frame streams 36.6 M point evaluations; inputs larger than L2"},
-                "ms_per_frame": {"detailed_output=False": results[False][False], "detailed_output=True": results[True][False]},
-                "e2e": {"value": world * n / (results[False][True] * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n * 24 + 128,
-                        "d2h_bytes_per_step": n * 16, "ms_per_frame_detailed": results[True][True]},
+                "ms_per_frame": {m: results[m][False] for m in results},
+                "ms_per_frame_e2e": {m: results[m][True] for m in results}, "d2h_bytes_per_frame": d2h,
+                "e2e": {"value": world * n / (results["plain"][True] * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": n * 24 + 128,
+                        "d2h_bytes_per_step": d2h.get("plain")},
                 "gpu_launches": 5 * 3 * args.steps,
                 "roofline": {"bound": "tensor", "kernel": "field_fwd (whole frame incl. compositing)", "achieved": tf, "peak": peaks["tf_sustained"],
                              "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"], "frac_burst": tf / peaks["tf_burst"], "traffic": None,
