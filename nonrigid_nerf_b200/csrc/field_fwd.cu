@@ -63,10 +63,15 @@ __device__ __forceinline__ uint32_t a_operand_offset(int step, uint32_t j) {
   return j * 8 * kChunkBytes;
 }
 
+// Developer profile (NRN_DEBUG_MODE=9): cycles CTA 0's roles spend waiting, read with nrn_debug_profile_fwd1().
+//   [0] issuer total  [1] issuer: a_ready  [3] issuer: w_full  [4] producer: w_empty  [5] epilogue WG (slot 0) total
+//   [6] epilogue: d_full  [10] slabs issued  [11] tile pairs
+__device__ unsigned long long g_fwd1_prof[16];
+
 struct Waiter {
   int* s_abort;
   int* g_err;
-  __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, int code) const {
+  __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, int code, unsigned long long* acc = nullptr) const {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
@@ -77,6 +82,7 @@ struct Waiter {
         return false;
       }
     }
+    if (acc) *acc += static_cast<unsigned long long>(clock64() - t0);
     return true;
   }
 };
@@ -186,11 +192,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
   tc_fence_after_sync();
   const uint32_t tmem_base = sh->tmem_base;
   const Waiter W{&sh->abort_flag, p.err};
+  const bool prof = p.debug_mode == 9 && blockIdx.x == 0;
 
   if (warp == 0) {
     // ===================== weight producer: global -> smem ring (bulk TMA) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      unsigned long long pw = 0;
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         uint32_t gb = 0, gn = 0;
 #pragma unroll 1
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           const uint8_t* src = step < 5 ? p.bend_w + gb : p.nerf_w + gn;
           for (int slot = 0; slot < 2; ++slot) {
             for (uint32_t j = 0; j < s.nslabs; ++j) {
-              W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
+              W.wait(&sh->w_empty[stage], phase ^ 1u, 101, prof ? &pw : nullptr);
               uint8_t* dst = ring + stage * kRingStageBytes;
               mbar_arrive_expect_tx(&sh->w_full[stage], s.slab_bytes);
               const uint8_t* g = src + j * s.slab_bytes;
@@ -213,25 +221,30 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           if (step < 5) gb += s.nslabs * s.slab_bytes; else gn += s.nslabs * s.slab_bytes;
         }
       }
+      if (prof) g_fwd1_prof[4] = pw;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t aph[2] = {0u, 0u};
+      unsigned long long w_a = 0, w_w = 0, n_slabs = 0, n_done = 0;
+      const long long t_start = clock64();
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        ++n_done;
 #pragma unroll 1
         for (int step = kFirstStep; step < 14; ++step) {
           const StepShape s = step_shape(step);
           const uint32_t idesc = umma_instr_desc(kTileM, s.N, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
           for (int slot = 0; slot < 2; ++slot) {
-            W.wait(&sh->a_ready[slot], aph[slot], 201);
+            W.wait(&sh->a_ready[slot], aph[slot], 201, prof ? &w_a : nullptr);
             aph[slot] ^= 1u;
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + slot * 256;
             const uint32_t a_base = smem_u32(act + slot * kSlotBytes);
             for (uint32_t j = 0; j < s.nslabs; ++j) {
-              W.wait(&sh->w_full[stage], phase, 202);
+              ++n_slabs;
+              W.wait(&sh->w_full[stage], phase, 202, prof ? &w_w : nullptr);
               tc_fence_after_sync();
               const uint64_t adesc = umma_smem_desc(a_base + a_operand_offset(step, j), kChunkBytes, 128);
               const uint64_t bdesc = umma_smem_desc(smem_u32(ring + stage * kRingStageBytes), s.N * 16, 128);
@@ -246,6 +259,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
           }
         }
       }
+      if (prof) {
+        g_fwd1_prof[0] = static_cast<unsigned long long>(clock64() - t_start);
+        g_fwd1_prof[1] = w_a; g_fwd1_prof[3] = w_w; g_fwd1_prof[10] = n_slabs; g_fwd1_prof[11] = n_done;
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue warpgroups =====================
@@ -257,13 +274,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
     uint8_t* e_row = Es + row * 16;
     const uint32_t taddr = tmem_base + ((static_cast<uint32_t>(warp & 3) * 32u) << 16) + slot * 256;
     uint32_t dph = 0;
+    unsigned long long w_d = 0;
+    const bool tprof = prof && slot == 0 && (threadIdx.x & 127) == 0;
+    const long long t_start = clock64();
     auto signal_ready = [&]() {
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&sh->a_ready[slot]);
     };
     auto wait_acc = [&](int code) {
-      W.wait(&sh->d_full[slot], dph, code);
+      W.wait(&sh->d_full[slot], dph, code, tprof ? &w_d : nullptr);
       dph ^= 1u;
       tc_fence_after_sync();
     };
@@ -427,6 +447,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
       // the next a_ready arrival is the next pair's prologue (which also means TMEM is drained)
     }
     if (p.stash && (threadIdx.x & 127) == 0) tma_bulk_wait<0>();   // all stash stores complete before the CTA exits
+    if (tprof) { g_fwd1_prof[5] = static_cast<unsigned long long>(clock64() - t_start); g_fwd1_prof[6] = w_d; }
   }
 
   tc_fence_before_sync();
@@ -435,6 +456,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) field_fwd_kernel(const FieldFw
 }
 
 // ------------------------------------------------------------------------------------------------
+extern "C" int nrn_debug_profile_fwd1(unsigned long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_fwd1_prof, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
+}
+
 size_t field_fwd_smem_bytes() { return 2 * kSlotBytes + kRingStages * kRingStageBytes + sizeof(Shared) + 64; }
 
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream) {

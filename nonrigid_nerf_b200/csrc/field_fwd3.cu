@@ -74,10 +74,16 @@ struct Shared3 {
   int abort_flag;
 };
 
+// Developer profile (NRN_DEBUG_MODE=9): cycles CTA 0's roles spend in each kind of wait, read with nrn_debug_profile().
+//   [0] issuer total  [1] issuer: a_ready[0]  [2] issuer: a_ready[1]  [3] issuer: w_full  [4] producer: w_empty
+//   [5] primary WG (slot 0) total  [6] primary: d_full[0]  [7] primary: a_free  [8] half-1 WG (slot 0) total  [9] half-1: d_full[1]
+//   [10] pieces issued  [11] tile pairs
+__device__ unsigned long long g_fwd3_prof[16];
+
 struct Waiter3 {
   int* s_abort;
   int* g_err;
-  __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, int code) const {
+  __device__ __forceinline__ bool wait(uint64_t* bar, uint32_t parity, int code, unsigned long long* acc = nullptr) const {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
@@ -88,6 +94,7 @@ struct Waiter3 {
         return false;
       }
     }
+    if (acc) *acc += static_cast<unsigned long long>(clock64() - t0);
     return true;
   }
 };
@@ -188,23 +195,27 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) field_fwd3_kernel(const Field
   tc_fence_after_sync();
   const uint32_t tmem_base = sh->tmem_base;
   const Waiter3 W{&sh->abort_flag, p.err};
+  const bool prof = p.debug_mode == 9 && blockIdx.x == 0;
 
   if (warp == 0) {
     // ===================== weight producer: global -> smem ring (bulk TMA) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      unsigned long long pw = 0;
+      unsigned long long* const ppw = prof ? &pw : nullptr;
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
 #pragma unroll 1
         for (int i = 0; i < sched.n; ++i) {
           const Piece pc = sched.p[i];
           const uint32_t bytes = static_cast<uint32_t>(pc.bytes_div16) * 16u;
           const uint8_t* src = (pc.bender ? p.bend_w : nerf_split) + pc.src_off;
-          W.wait(&sh->w_empty[stage], phase ^ 1u, 101);
+          W.wait(&sh->w_empty[stage], phase ^ 1u, 101, ppw);
           mbar_arrive_expect_tx(&sh->w_full[stage], bytes);
           tma_bulk_g2s(ring + stage * kStageBytes3, src, bytes, &sh->w_full[stage]);
           if (++stage == kStages3) { stage = 0; phase ^= 1u; }
         }
       }
+      if (prof) g_fwd3_prof[4] = pw;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -212,13 +223,17 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) field_fwd3_kernel(const Field
       uint32_t stage = 0, phase = 0;
       uint32_t aph[2] = {0u, 0u};
       const uint32_t a_base0 = smem_u32(act), a_base1 = smem_u32(act + kSlotBytes);
+      unsigned long long w_a0 = 0, w_a1 = 0, w_w = 0, n_pieces = 0, n_pairs_done = 0;
+      const long long t_start = clock64();
       for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        ++n_pairs_done;
 #pragma unroll 1
         for (int i = 0; i < sched.n; ++i) {
           const Piece pc = sched.p[i];
-          if (pc.wait0) { W.wait(&sh->a_ready[0], aph[0], 201); aph[0] ^= 1u; }
-          if (pc.wait1) { W.wait(&sh->a_ready[1], aph[1], 203); aph[1] ^= 1u; }
-          W.wait(&sh->w_full[stage], phase, 202);
+          ++n_pieces;
+          if (pc.wait0) { W.wait(&sh->a_ready[0], aph[0], 201, prof ? &w_a0 : nullptr); aph[0] ^= 1u; }
+          if (pc.wait1) { W.wait(&sh->a_ready[1], aph[1], 203, prof ? &w_a1 : nullptr); aph[1] ^= 1u; }
+          W.wait(&sh->w_full[stage], phase, 202, prof ? &w_w : nullptr);
           tc_fence_after_sync();
           const uint32_t n = pc.n;
           const uint32_t idesc = umma_instr_desc(kTileM, n, UMMA_F16, UMMA_F16, UMMA_K_MAJOR, UMMA_K_MAJOR);
@@ -241,6 +256,10 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) field_fwd3_kernel(const Field
           if (++stage == kStages3) { stage = 0; phase ^= 1u; }
         }
       }
+      if (prof) {
+        g_fwd3_prof[0] = static_cast<unsigned long long>(clock64() - t_start);
+        g_fwd3_prof[1] = w_a0; g_fwd3_prof[2] = w_a1; g_fwd3_prof[3] = w_w; g_fwd3_prof[10] = n_pieces; g_fwd3_prof[11] = n_pairs_done;
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue warpgroups: (slot, output half) =====================
@@ -256,13 +275,16 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) field_fwd3_kernel(const Field
     const bool wg_leader = (threadIdx.x & 127) == 0;
     const int bar_id = 1 + wg;               // named barrier of this warpgroup
     uint32_t dph = 0, fph = 0;
+    unsigned long long w_d = 0, w_f = 0;
+    const bool tprof = prof && slot == 0 && (threadIdx.x & 127) == 0;
+    const long long t_start = clock64();
     auto signal_ready = [&]() {
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(&sh->a_ready[half]);
     };
     auto wait_acc = [&](int code) {
-      W.wait(&sh->d_full[half], dph, code);
+      W.wait(&sh->d_full[half], dph, code, tprof ? &w_d : nullptr);
       dph ^= 1u;
       tc_fence_after_sync();
     };
@@ -408,7 +430,7 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) field_fwd3_kernel(const Field
 #pragma unroll 1
       for (int L = 0; L < 8; ++L) {
         wait_acc(310 + L);
-        W.wait(&sh->a_free, fph, 340 + L);
+        W.wait(&sh->a_free, fph, 340 + L, tprof ? &w_f : nullptr);
         fph ^= 1u;
         stash_begin();
         if (p.debug_mode != 1) epi3_bias_relu_store<128>(taddr, p.nerf_bias + L * 256, h_row);
@@ -432,6 +454,11 @@ __global__ void __launch_bounds__(kFwd3Threads, 1) field_fwd3_kernel(const Field
       }
     }
     if (p.stash && (threadIdx.x & 127) == 0) tma_bulk_wait<0>();
+    if (tprof) {
+      const unsigned long long tot = static_cast<unsigned long long>(clock64() - t_start);
+      if (half == 0) { g_fwd3_prof[5] = tot; g_fwd3_prof[6] = w_d; g_fwd3_prof[7] = w_f; }
+      else { g_fwd3_prof[8] = tot; g_fwd3_prof[9] = w_d; }
+    }
   }
 
   tc_fence_before_sync();
@@ -508,6 +535,10 @@ Schedule build_schedule(bool has_bender) {
 bool g_sched_uploaded[64] = {};
 
 }  // namespace
+
+extern "C" int nrn_debug_profile_fwd3(unsigned long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_fwd3_prof, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
+}
 
 size_t field_fwd3_smem_bytes() { return 2 * kSlotBytes + kStages3 * kStageBytes3 + sizeof(Shared3) + 64; }
 

@@ -232,7 +232,8 @@ class RayShardedFunction:
         def shard(t: torch.Tensor):
             if t.dim() == 0 or t.shape[0] != n:
                 return t
-            if self.broadcast_inputs and not t.requires_grad:
+            # host tensors cannot travel over an NCCL-only group: they are taken as identical on every rank
+            if self.broadcast_inputs and not t.requires_grad and (t.is_cuda or dist.get_backend() != "nccl"):
                 t = t.contiguous()
                 dist.broadcast(t, src=0)
             return t[lo:hi]
@@ -295,11 +296,11 @@ class training_wrapper_class(torch.nn.Module):
             # exact_divergence = False, backprop_into_weights = False (train.py:246-247); fused closed-form kernel
             # weights 1 - exp(-relu(opacity_alpha)) (train.py:267) are formed inside the kernels
             # Hutchinson probes: torch.randn like run_nerf_helpers.py:110, or injected with the other random draws
-            # (render_kwargs_train["randomness"]["e"], [N * N_samples, 3]) for exact reproduction
+            # (render_kwargs_train["randomness"]["e"], [N, N_samples, 3] or [N * N_samples, 3]) for exact reproduction
             rnd = render_kwargs_train.get("randomness")
             probes = rnd.get("e") if isinstance(rnd, dict) else None
             div = _ag.divergence_loss(extras["unmasked_offsets"], extras["rigidity_mask"], None, self.ray_bender,
-                                      e=None if probes is None else probes.to(dev), opacity_alpha=extras["opacity_alpha"])
+                                      e=None if probes is None else probes.to(dev).reshape(-1, 3), opacity_alpha=extras["opacity_alpha"])
             loss = loss + (args.divergence_loss_weight * sched) * div
         return loss
 

@@ -40,8 +40,9 @@ def _build(dev, g):
     seed, n = int(g["seed"]), int(g["n"])
     coarse, fine, bender, _ = helpers.build_models(O, seed, dev)
     r = O.make_rays(seed, n)
-    rnd = dict(O.make_randomness(seed, n, 64, 64))
-    rnd["e"] = torch.from_numpy(g["e"])
+    # per-ray random draws on the device, leading dimension = rays: RayShardedFunction shards them with their rays
+    rnd = {k: v.to(dev) for k, v in O.make_randomness(seed, n, 64, 64).items()}
+    rnd["e"] = torch.from_numpy(g["e"]).to(dev).view(n, 64, 3)
     latents = [torch.from_numpy(row.copy()).to(dev).requires_grad_(True) for row in g["latent_table"]]
     params = latents + list(bender.parameters()) + list(coarse.parameters()) + list(fine.parameters())
     opt = optim.Adam(params, lr=5e-4)

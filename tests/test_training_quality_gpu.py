@@ -1,0 +1,33 @@
+"""Training quality guard (north_star: PSNR within the reference's): a short A/B of scripts/train_ab.py -- this repository's
+path vs the fp32 oracle (run on the GPU as the checker) from the same initialisation, batches and random draws, all three
+regularisers on.  Two fp32-class trainings of this scene already drift apart by several tenths of a dB after a few hundred
+iterations (profiles/r02_train_ab*.json: oracle fp32 vs oracle TF32), so the assertions are statistical guards, not
+bit-level claims: the loss level reached must agree within a few percent, the held-out PSNR must not be worse than the
+oracle's beyond that noise, and on identical TRAINED weights (large PE-frequency sensitivity) the two renderers must agree."""
+import argparse
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_short_training_matches_the_fp32_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import train_ab
+    args = argparse.Namespace(iters=150, n_rand=1024, out=None, no_tf32_run=True, seeds=1)
+    runs = [train_ab.run_once(args, seed=12 + 101 * k, with_tf32=False, curves=False) for k in range(2)]
+    for r in runs:
+        a, b = r["psnr_held_out"]["A_this_repo_fp16"], r["psnr_held_out"]["B_oracle_fp32"]
+        la, lb = r["mean_loss_last_tenth"]["A"], r["mean_loss_last_tenth"]["B"]
+        par = r["trained_weights_render_parity"]
+        print(f"held-out PSNR: this repo {a:.2f} dB, oracle {b:.2f} dB; final loss {la:.5f} vs {lb:.5f}; "
+              f"same trained weights: rgb L-inf {par['rgb_linf_this_repo_vs_oracle_on_B_weights']:.2e}, "
+              f"PSNR {par['psnr_this_repo_vs_oracle_on_B_weights']:.1f} dB")
+        assert abs(la - lb) <= 0.06 * lb, (la, lb)
+        assert a >= b - 0.6, (a, b)
+        assert par["psnr_this_repo_vs_oracle_on_B_weights"] >= 55.0 and par["rgb_linf_this_repo_vs_oracle_on_B_weights"] <= 5e-2
+    mean_delta = sum(r["delta_psnr_A_minus_B"] for r in runs) / len(runs)
+    assert mean_delta >= -0.4, mean_delta
