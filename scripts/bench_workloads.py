@@ -121,10 +121,14 @@ def run(args, rank, local_rank, world):
                              "peak_source": peaks["source"]}}
         if not args.no_cpu_baseline:
             from oracle import reference_arm as RA
-            threads = os.cpu_count() or 1
-            rate, sec, kind = RA.render_rate(8192, 2, threads, False)
-            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": kind,
-                                    "sample": "8192 rays of the same test-time render (64c+128f), 1 warm-up + median of 2"}
+            host = os.cpu_count() or 1
+            cands = sorted({c for c in (host, 64, 32, 16) if c <= host}, reverse=True)
+            calib = {c: RA.render_rate(512, 1, c, False)[0] for c in cands}      # same thread calibration as the training arm
+            threads = max(calib, key=calib.get)
+            rate, sec, kind = RA.render_rate(4096, 2, threads, False)
+            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": threads, "kind": kind, "host_cores": host,
+                                    "calibration_rays_per_s_by_threads": {str(k): v for k, v in calib.items()},
+                                    "sample": "4096 rays of the same test-time render (64c+128f), 1 warm-up + median of 2"}
         print(json.dumps(line), flush=True)
         return
 
