@@ -128,7 +128,7 @@ def cpu_baseline(n_rays, steps, warmup):
     on a 256-ray slice picks among {all cores, 64, 32, 16}; the timed run is the full n_rays-ray step at that count."""
     from oracle import reference_arm as RA
     host = os.cpu_count() or 1
-    cands = sorted({c for c in (host, 64, 32, 16) if c <= host}, reverse=True)
+    cands = sorted({c for c in (host, 64, 32, 16, 8) if c <= host}, reverse=True)
     calib = {}
     for c in cands:
         calib[c] = RA.training_rate(synth_batch, 256, 1, 1, c, make_args())[0]
@@ -412,10 +412,11 @@ def main():
                    "inputs": "every rank draws the global batch from the shared seed and uploads its own row block from pinned memory",
                    "l2": "per-step working set (activation + gradient stash, ~1.9 GB at 1024 rays) exceeds the 126 MB L2; 8 rotating input batches"},
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
-        "gpu_launches": (33 if world == 1 else 40) * args.steps,
-        # this repo's kernels per step: 3 weight packs, 1 coarse sampler, 2 field forwards, 2 composites, 1 ray loss + 4 scalings,
-        # 3 divergence, 2 composite backwards, 2 + 2 absmax, 2 field DGRADs, 3 WGRADs + 3 reductions, 2 optimizer
-        # (N GPUs: 3 peer reduce+Adam, 3 loss gather instead of the 2 optimizer launches)
+        "gpu_launches": (32 if world == 1 else 36) * args.steps,
+        # this repo's kernels per step, counted in profiles/r02_launches_step.csv (32 of the step's 63 launches, 94 % of its GPU
+        # time): 3 weight packs, 1 coarse sampler, 2 field forwards, 2 composites, 1 ray loss + 4 scalings, 3 divergence, 2
+        # composite backwards, 4 absmax, 2 field DGRADs, 3 WGRADs + 3 reductions, 2 optimizer (N GPUs: 3 peer reduce + Adam and
+        # 3 loss-gather launches instead of the 2 optimizer launches)
         "kernel_ms_per_step": per_step, "ms_per_step_instrumented": (ms_instrumented / args.steps) if ms_instrumented else None,
         "cuda_graph": graphed is not None, "whole_step_in_graph": graphed is not None and fused_collectives,
         "step_tflops_algorithmic": step_tf, "step_frac_of_sustained_peak": step_tf / peaks["tf_sustained"],

@@ -79,45 +79,40 @@ __device__ __forceinline__ uint32_t pk(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// out[j] = sum_k W[j][k] in[k]  (W row-major [OUT][IN] in smem, `in` in registers), out -> act column.
-// Eight outputs at a time: eight independent FMA chains per thread (the block runs only 4 warps per SM sub-partition pair, so the
-// instruction-level parallelism has to come from inside the thread); per output the k order is unchanged.
+// out[j] = sum_k W[j][k] in[k]  (W row-major [OUT][IN] in smem, `in` in registers), out -> act column
 template <int IN>
 __device__ __forceinline__ void matvec(const float* W, const float (&in)[IN], float* act, int OUT) {
 #pragma unroll 1
-  for (int j0 = 0; j0 < OUT; j0 += 8) {
-    float a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  for (int j0 = 0; j0 < OUT; j0 += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int k = 0; k < IN; k += 4) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 w = *reinterpret_cast<const float4*>(W + (j0 + i) * IN + k);
-        a[i] += w.x * in[k] + w.y * in[k + 1] + w.z * in[k + 2] + w.w * in[k + 3];
-      }
+      const float4 w0 = *reinterpret_cast<const float4*>(W + (j0 + 0) * IN + k);
+      const float4 w1 = *reinterpret_cast<const float4*>(W + (j0 + 1) * IN + k);
+      const float4 w2 = *reinterpret_cast<const float4*>(W + (j0 + 2) * IN + k);
+      const float4 w3 = *reinterpret_cast<const float4*>(W + (j0 + 3) * IN + k);
+      a0 += w0.x * in[k] + w0.y * in[k + 1] + w0.z * in[k + 2] + w0.w * in[k + 3];
+      a1 += w1.x * in[k] + w1.y * in[k + 1] + w1.z * in[k + 2] + w1.w * in[k + 3];
+      a2 += w2.x * in[k] + w2.y * in[k + 1] + w2.z * in[k + 2] + w2.w * in[k + 3];
+      a3 += w3.x * in[k] + w3.y * in[k + 1] + w3.z * in[k + 2] + w3.w * in[k + 3];
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) act[(j0 + i) * kDivThreads] = a[i];
+    act[(j0 + 0) * kDivThreads] = a0; act[(j0 + 1) * kDivThreads] = a1;
+    act[(j0 + 2) * kDivThreads] = a2; act[(j0 + 3) * kDivThreads] = a3;
   }
 }
-// out[k] = sum_j W[j][k] in[j]  (transposed product; W row-major [NJ][NK] in smem); eight outputs at a time
+// out[k] = sum_j W[j][k] in[j]  (transposed product; W row-major [NJ][NK] in smem)
 template <int NJ>
 __device__ __forceinline__ void matvec_t(const float* W, const float (&in)[NJ], float* act, int NK) {
 #pragma unroll 1
-  for (int k0 = 0; k0 < NK; k0 += 8) {
-    float a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  for (int k0 = 0; k0 < NK; k0 += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const float4 w0 = *reinterpret_cast<const float4*>(W + j * NK + k0);
-      const float4 w1 = *reinterpret_cast<const float4*>(W + j * NK + k0 + 4);
-      a[0] += w0.x * in[j]; a[1] += w0.y * in[j]; a[2] += w0.z * in[j]; a[3] += w0.w * in[j];
-      a[4] += w1.x * in[j]; a[5] += w1.y * in[j]; a[6] += w1.z * in[j]; a[7] += w1.w * in[j];
+      const float4 w = *reinterpret_cast<const float4*>(W + j * NK + k0);
+      a0 += w.x * in[j]; a1 += w.y * in[j]; a2 += w.z * in[j]; a3 += w.w * in[j];
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) act[(k0 + i) * kDivThreads] = a[i];
+    act[(k0 + 0) * kDivThreads] = a0; act[(k0 + 1) * kDivThreads] = a1;
+    act[(k0 + 2) * kDivThreads] = a2; act[(k0 + 3) * kDivThreads] = a3;
   }
 }
 // masked copy act column -> registers, and fp16 image chunks [chunk0, chunk0 + N/8) of this row

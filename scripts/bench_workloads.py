@@ -122,7 +122,7 @@ def run(args, rank, local_rank, world):
         if not args.no_cpu_baseline:
             from oracle import reference_arm as RA
             host = os.cpu_count() or 1
-            cands = sorted({c for c in (host, 64, 32, 16) if c <= host}, reverse=True)
+            cands = sorted({c for c in (host, 64, 32, 16, 8) if c <= host}, reverse=True)
             calib = {c: RA.render_rate(512, 1, c, False)[0] for c in cands}      # same thread calibration as the training arm
             threads = max(calib, key=calib.get)
             rate, sec, kind = RA.render_rate(4096, 2, threads, False)
