@@ -47,13 +47,6 @@ int nrn_pack_bender(const float* const* net_w /*5*/, const float* const* net_b /
                     const float* const* rig_w /*3*/, const float* const* rig_b /*3*/, int latent_size,
                     void* packed, void* stream);
 
-/* Developer knob: which forward field kernel nrn_field_forward launches on the current device (results are bit-identical):
- * 1 = two independent tile slots per CTA (field_fwd.cu), 2 = CTA pair / cta_group::2 (field_fwd2.cu), 3 = shared-slab
- * schedule with half-layer pipelining (field_fwd3.cu).  The default can also be set with the environment variable NRN_FWD. */
-int nrn_select_forward_kernel(int kind);
-/* Likewise for the DGRAD kernel nrn_field_backward launches: 1 = field_bwd.cu, 3 = field_bwd3.cu (environment: NRN_BWD). */
-int nrn_select_backward_kernel(int kind);
-
 /* ---- ray generation: get_rays / get_rays_np (run_nerf_helpers.py:588-622) on the device -----------------------------
  * c2w [3][4] row-major, intrinsics = (focal_x, focal_y, center_x, center_y); rays_o / rays_d [H*W][3] in the [H, W, 3]
  * order of the reference.  Bit-identical to the reference's float32 arithmetic. */

@@ -116,8 +116,6 @@ SYMBOLS = {
     "nrn_pack_nerf": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int, _vp, _vp]),
     "nrn_pack_bender": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.c_int, _vp, _vp]),
     "nrn_sample_coarse": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
-    "nrn_select_forward_kernel": (C.c_int, [C.c_int]),
-    "nrn_select_backward_kernel": (C.c_int, [C.c_int]),
     "nrn_get_rays": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "nrn_ray_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nrn_median_visibility_index": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),

@@ -16,10 +16,7 @@
 
 namespace nrn {
 cudaError_t launch_field_fwd(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
-cudaError_t launch_field_fwd2(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
-cudaError_t launch_field_fwd3(const FieldFwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
 cudaError_t launch_field_bwd(const FieldBwdParams& p, bool has_bender, int num_sms, cudaStream_t stream);
-cudaError_t launch_field_bwd3(const FieldBwdParams& p, const uint8_t* nerf_packed_base, bool has_bender, int num_sms, cudaStream_t stream);
 }
 
 namespace {
@@ -41,8 +38,6 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
   int* err_word = nullptr;   // [0] error word, [1] loss-scale source (float) of the running backward
   int num_sms = 0;
-  int fwd_kind = 1;          // 1 field_fwd.cu, 2 field_fwd2.cu (CTA pair), 3 field_fwd3.cu (shared-slab schedule)
-  int bwd_kind = 1;          // 1 field_bwd.cu, 3 field_bwd3.cu (shared-slab schedule)
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -59,13 +54,6 @@ int device_state(DeviceState** out) {
     if (prop.major != 10) return fail(NRN_E_INVALID, "nrnerf_b200 needs an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
     s.num_sms = prop.multiProcessorCount;
     if (const char* g = getenv("NRN_GRID")) { const int v = atoi(g); if (v > 0 && v < s.num_sms) s.num_sms = v; }   // developer experiments
-    // forward field kernel: single-CTA kernel (field_fwd.cu) by default; NRN_PAIR=1 selects the CTA-pair kernel
-    // (field_fwd2.cu, tcgen05 cta_group::2), which measures within +-5% of it
-    s.fwd_kind = 1;
-    if (const char* g = getenv("NRN_PAIR")) s.fwd_kind = atoi(g) != 0 ? 2 : 1;
-    if (const char* g = getenv("NRN_FWD")) { const int v = atoi(g); if (v >= 1 && v <= 3) s.fwd_kind = v; }
-    s.bwd_kind = 1;
-    if (const char* g = getenv("NRN_BWD")) { const int v = atoi(g); if (v == 1 || v == 3) s.bwd_kind = v; }
     e = cudaMalloc(&s.err_word, 4 * sizeof(int));
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(err word)");
     e = cudaMemset(s.err_word, 0, 4 * sizeof(int));
@@ -170,24 +158,6 @@ int nrn_sample_coarse(const float* rays, const float* t_rand, int n_rays, int n_
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "sample_coarse_kernel");
 }
 
-int nrn_select_forward_kernel(int kind) {
-  if (kind < 1 || kind > 3) return fail(NRN_E_INVALID, "nrn_select_forward_kernel: kind %d (1 = two independent slots, 2 = CTA pair, 3 = shared-slab schedule)", kind);
-  DeviceState* ds;
-  const int rc = device_state(&ds);
-  if (rc) return rc;
-  ds->fwd_kind = kind;
-  return NRN_OK;
-}
-
-int nrn_select_backward_kernel(int kind) {
-  if (kind != 1 && kind != 3) return fail(NRN_E_INVALID, "nrn_select_backward_kernel: kind %d (1 = two independent slots, 3 = shared-slab schedule)", kind);
-  DeviceState* ds;
-  const int rc = device_state(&ds);
-  if (rc) return rc;
-  ds->bwd_kind = kind;
-  return NRN_OK;
-}
-
 int nrn_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, float* rays_d, void* stream) {
   if (H < 0 || W < 0) return fail(NRN_E_INVALID, "nrn_get_rays: bad sizes");
   if (H == 0 || W == 0) return NRN_OK;
@@ -258,10 +228,7 @@ int nrn_field_forward(const NrnFieldArgs* a) {
   cudaError_t e;
   {
     ScopedTimer tm(0, static_cast<cudaStream_t>(a->stream));
-    const bool bend = a->bender_packed != nullptr;
-    cudaStream_t st = static_cast<cudaStream_t>(a->stream);
-    e = ds->fwd_kind == 3 ? nrn::launch_field_fwd3(p, bend, ds->num_sms, st)
-        : ds->fwd_kind == 2 ? nrn::launch_field_fwd2(p, bend, ds->num_sms, st) : nrn::launch_field_fwd(p, bend, ds->num_sms, st);
+    e = nrn::launch_field_fwd(p, a->bender_packed != nullptr, ds->num_sms, static_cast<cudaStream_t>(a->stream));
   }
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "field_fwd_kernel");
 }
@@ -308,7 +275,7 @@ int nrn_composite_backward(const NrnCompositeBwdArgs* a) {
 static long long even_tiles(int n_rays, int n_samples) {
   const long long P = static_cast<long long>(n_rays) * n_samples;
   const long long tiles = (P + nrn::kTileM - 1) / nrn::kTileM;
-  return (tiles + 3) & ~3LL;   // the kernels work on groups of four tiles (two slots x a CTA pair)
+  return (tiles + 1) & ~1LL;   // the kernels work on tile pairs (two slots per CTA)
 }
 size_t nrn_stash_bytes(int n_rays, int n_samples) { return static_cast<size_t>(even_tiles(n_rays, n_samples)) * nrn::kStashTileBytes; }
 size_t nrn_grad_stash_bytes(int n_rays, int n_samples) { return static_cast<size_t>(even_tiles(n_rays, n_samples)) * nrn::kGradTileBytes; }
@@ -366,11 +333,7 @@ int nrn_field_backward(const NrnFieldBwdArgs* a) {
   if (e == cudaSuccess && bend && p.d_unmasked_up) e = nrn::launch_absmax(p.d_unmasked_up, p.P * 3, amax, st, true);
   if (e == cudaSuccess && bend && p.d_rigid_up) e = nrn::launch_absmax(p.d_rigid_up, p.P, amax, st, true);
   if (e != cudaSuccess) return cuda_fail(e, "absmax_kernel");
-  {
-    ScopedTimer tm(1, st);
-    e = ds->bwd_kind == 3 ? nrn::launch_field_bwd3(p, static_cast<const uint8_t*>(a->nerf_packed), bend, ds->num_sms, st)
-                          : nrn::launch_field_bwd(p, bend, ds->num_sms, st);
-  }
+  { ScopedTimer tm(1, st); e = nrn::launch_field_bwd(p, bend, ds->num_sms, st); }
   if (e != cudaSuccess) return cuda_fail(e, "field_bwd_kernel");
   nrn::WgradParams w{};
   w.stash = p.stash; w.gstash = p.gstash; w.scratch = a->wgrad_scratch; w.amax = amax; w.n_tiles = p.n_tiles; w.err = ds->err_word;

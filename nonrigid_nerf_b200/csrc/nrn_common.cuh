@@ -94,15 +94,7 @@ constexpr int kBendTB2Bytes = 10 * 96 * 16;
 constexpr int kBendTB1Bytes = 12 * 96 * 16;
 constexpr int kBendTB0Bytes = 12 * 48 * 16;
 constexpr int kBendTWBytes = kBendTB4Bytes + kBendTB3Bytes + kBendTB2Bytes + kBendTB1Bytes + kBendTB0Bytes;
-// split-order forward image (field_fwd3.cu): per layer, per output half of 128 rows, K pieces of 64: [8 chunks][128 rows][8]
-// (L0: 2 pieces, L1-4 / L6-7: 8, L5: 10; the embedding's K piece first), then the head [32 chunks][16 rows][8]; same bytes
-// as the forward images, streaming order of the shared-slab kernel
-constexpr int kNerfSOffset = kNerfTOffset + kNerfTWBytes;
-// split-order transposed image (field_bwd3.cu): head^T as 2 pieces [2 chunks][128 rows][8]; L7^T, L6^T, L5h^T, L4^T..L1^T as
-// (output half, K piece of 64) pieces [8 chunks][128 rows][8]; L5e^T and L0^T (64 rows) unchanged; same order of layers and
-// the same bytes as the transposed images
-constexpr int kNerfTSOffset = kNerfSOffset + kNerfWBytes;
-constexpr int kNerfPackedBytes = kNerfTSOffset + kNerfTWBytes;
+constexpr int kNerfPackedBytes = kNerfTOffset + kNerfTWBytes;
 constexpr int kBendPackedBytes = kBendTOffset + kBendTWBytes;
 
 struct FieldBwdParams {

@@ -163,96 +163,13 @@ __device__ __forceinline__ void pack_bender_t_elem(const int idx, const BenderSr
 }
 
 
-// ---- split-order forward image (field_fwd3.cu): (layer, output half, K piece of 64) -> [8 chunks][128 rows][8] ----
-__device__ __forceinline__ void pack_nerf_split_elem(const int idx, const NerfSrc& src, int in_ch, int out_ch, __half* __restrict__ w) {
-  if (idx >= kNerfWBytes / 2) return;
-  constexpr int piece = 8 * 128 * 8;          // elements per piece
-  constexpr int n_main = (2 + 6 * 8 + 10) * piece;
-  float v = 0.f;
-  if (idx < n_main) {
-    int pi = idx / piece;                      // piece index in streaming order
-    const int rem = idx - pi * piece;
-    const int c = rem / (128 * 8), r = (rem >> 3) & 127, e = rem & 7;
-    int L = 0;
-    for (;; ++L) {
-      const int np = L == 0 ? 2 : (L == 5 ? 10 : 8);
-      if (pi < np) break;
-      pi -= np;
-    }
-    const int nk = L == 0 ? 1 : (L == 5 ? 5 : 4);
-    const int nh = pi / nk, ks = pi - nh * nk;
-    const int row = nh * 128 + r;
-    const int k = ks * 64 + c * 8 + e;         // column inside the layer's padded K
-    if (L == 0) v = k < in_ch ? src.w[0][row * in_ch + k] : 0.f;
-    else if (L == 5) {
-      const int ld = in_ch + 256;
-      if (k < 64) v = k < in_ch ? src.w[5][row * ld + k] : 0.f;
-      else v = src.w[5][row * ld + in_ch + (k - 64)];
-    } else v = src.w[L][row * 256 + k];
-  } else {                                     // head, N padded to 16
-    int k, r;
-    decode(idx - n_main, 16, k, r);
-    v = r < out_ch ? src.w[8][r * 256 + k] : 0.f;
-  }
-  w[idx] = __float2half_rn(v);
-}
-
-// ---- split-order transposed image (field_bwd3.cu) ----
-// r = input feature (row of W^T), k = output feature
-__device__ __forceinline__ void pack_nerf_ts_elem(const int idx, const NerfSrc& src, int in_ch, int out_ch, __half* __restrict__ w) {
-  if (idx >= kNerfTWBytes / 2) return;
-  constexpr int nh = kNerfTHeadBytes / 2, nl = kNerfLBytes / 2, ne = kNerfTEBytes / 2;
-  constexpr int piece = 8 * 128 * 8;
-  int i = idx;
-  float v = 0.f;
-  const int ld5 = in_ch + 256;
-  auto main_piece = [&](int j, int& r, int& k) {   // j: element index inside a 256 x 256 layer in (half, K piece) order
-    const int pi = j / piece, rem = j - pi * piece;
-    const int half = pi >> 2, ks = pi & 3;
-    const int c = rem / (128 * 8);
-    r = half * 128 + ((rem >> 3) & 127);
-    k = ks * 64 + c * 8 + (rem & 7);
-  };
-  int r, k;
-  if (i < nh) {                           // head^T: two pieces [2 chunks][128 rows][8], K = out_ch padded to 16
-    const int half = i / (2 * 128 * 8), rem = i - half * 2 * 128 * 8;
-    const int c = rem / (128 * 8);
-    r = half * 128 + ((rem >> 3) & 127);
-    k = c * 8 + (rem & 7);
-    v = k < out_ch ? src.w[8][k * 256 + r] : 0.f;
-  } else if ((i -= nh) < 2 * nl) {        // L7^T, L6^T
-    const int L = 7 - i / nl;
-    main_piece(i % nl, r, k);
-    v = src.w[L][k * 256 + r];
-  } else if ((i -= 2 * nl) < ne) {        // L5e^T (64 rows): unchanged layout
-    decode(i, 64, k, r);
-    v = r < in_ch ? src.w[5][k * ld5 + r] : 0.f;
-  } else if ((i -= ne) < nl) {            // L5h^T
-    main_piece(i, r, k);
-    v = src.w[5][k * ld5 + in_ch + r];
-  } else if ((i -= nl) < 4 * nl) {        // L4^T .. L1^T
-    const int L = 4 - i / nl;
-    main_piece(i % nl, r, k);
-    v = src.w[L][k * 256 + r];
-  } else {                                // L0^T (64 rows): unchanged layout
-    i -= 4 * nl;
-    decode(i, 64, k, r);
-    v = r < in_ch ? src.w[0][k * in_ch + r] : 0.f;
-  }
-  w[idx] = __float2half_rn(v);
-}
-
 // one launch per module: the first blocks write the forward images (+ biases), the rest the transposed images
 constexpr int kPackThreads = 256;
 __global__ void __launch_bounds__(kPackThreads) pack_nerf_kernel(NerfSrc src, int in_ch, int out_ch, __half* __restrict__ w,
-                                                                 float* __restrict__ bias, __half* __restrict__ wt, __half* __restrict__ ws,
-                                                                 __half* __restrict__ wts) {
+                                                                 float* __restrict__ bias, __half* __restrict__ wt) {
   constexpr int nb_fwd = (kNerfWBytes / 2 + kPackThreads - 1) / kPackThreads;
-  constexpr int nb_t = (kNerfTWBytes / 2 + kPackThreads - 1) / kPackThreads;
   if (blockIdx.x < nb_fwd) pack_nerf_elem(blockIdx.x * kPackThreads + threadIdx.x, src, in_ch, out_ch, w, bias);
-  else if (blockIdx.x < nb_fwd + nb_t) pack_nerf_t_elem((blockIdx.x - nb_fwd) * kPackThreads + threadIdx.x, src, in_ch, out_ch, wt);
-  else if (blockIdx.x < 2 * nb_fwd + nb_t) pack_nerf_split_elem((blockIdx.x - nb_fwd - nb_t) * kPackThreads + threadIdx.x, src, in_ch, out_ch, ws);
-  else pack_nerf_ts_elem((blockIdx.x - 2 * nb_fwd - nb_t) * kPackThreads + threadIdx.x, src, in_ch, out_ch, wts);
+  else pack_nerf_t_elem((blockIdx.x - nb_fwd) * kPackThreads + threadIdx.x, src, in_ch, out_ch, wt);
 }
 __global__ void __launch_bounds__(kPackThreads) pack_bender_kernel(BenderSrc src, __half* __restrict__ w, float* __restrict__ bias,
                                                                    __half* __restrict__ wt) {
@@ -266,10 +183,9 @@ __global__ void __launch_bounds__(kPackThreads) pack_bender_kernel(BenderSrc src
 // packed = [forward images | biases | transposed images] (offsets in nrn_common.cuh)
 cudaError_t launch_pack_nerf(const NerfSrc& src, int in_ch, int out_ch, void* packed, cudaStream_t st) {
   uint8_t* base = reinterpret_cast<uint8_t*>(packed);
-  const int nb = 2 * ((kNerfWBytes / 2 + kPackThreads - 1) / kPackThreads) + 2 * ((kNerfTWBytes / 2 + kPackThreads - 1) / kPackThreads);
+  const int nb = (kNerfWBytes / 2 + kPackThreads - 1) / kPackThreads + (kNerfTWBytes / 2 + kPackThreads - 1) / kPackThreads;
   pack_nerf_kernel<<<nb, kPackThreads, 0, st>>>(src, in_ch, out_ch, reinterpret_cast<__half*>(base),
-                                               reinterpret_cast<float*>(base + kNerfWBytes), reinterpret_cast<__half*>(base + kNerfTOffset),
-                                               reinterpret_cast<__half*>(base + kNerfSOffset), reinterpret_cast<__half*>(base + kNerfTSOffset));
+                                               reinterpret_cast<float*>(base + kNerfWBytes), reinterpret_cast<__half*>(base + kNerfTOffset));
   return cudaGetLastError();
 }
 cudaError_t launch_pack_bender(const BenderSrc& src, void* packed, cudaStream_t st) {

@@ -134,139 +134,3 @@ def test_sample_coarse_matches_oracle():
     np.testing.assert_allclose(z0.cpu().numpy(), O.stratified_z(near, far, s, None).numpy(), atol=1.3e-7, rtol=0)
     zl = ops.sample_coarse(helpers.rays8(r, dev), s, None, True)
     np.testing.assert_allclose(zl.cpu().numpy(), O.stratified_z(near, far, s, None, lindisp=True).numpy(), rtol=2e-6)
-
-
-def test_cta_pair_forward_kernel_matches_the_single_cta_kernel(tmp_path):
-    """field_fwd2.cu (tcgen05 cta_group::2, NRN_PAIR=1) is a second implementation of the same arithmetic: identical
-    MMA K order and epilogue, so its raw output and point details must equal the default kernel's bit for bit.
-    The choice is read once per process, hence the subprocess."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    script = r"""
-import sys, torch
-sys.path.insert(0, %r)
-import oracle.nrnerf_oracle as O
-from tests import helpers
-from nonrigid_nerf_b200 import autograd as ag, ops, _lib
-dev = torch.device("cuda:0")
-coarse, fine, bender, _ = helpers.build_models(O, 11, dev, True)
-out = {}
-for n, s in ((37, 64), (300, 128)):
-    r = O.make_rays(11, n)
-    rays = helpers.rays8(r, dev)
-    z = ops.sample_coarse(rays, s, None, False)
-    for with_b in (True, False):
-        coarse.ray_bender = (bender if with_b else None,)
-        res = ag.field_rays(coarse, rays, z, r["latents"].to(dev) if with_b else None, True)
-        raw = res[0] if isinstance(res, (tuple, list)) else res
-        out[f"raw_{n}_{s}_{int(with_b)}"] = raw.detach().cpu()
-_lib.device_error_check()
-torch.save(out, sys.argv[1])
-""" % root
-    outs = []
-    for pair in ("0", "1"):
-        path = str(tmp_path / f"pair{pair}.pt")
-        env = dict(os.environ, NRN_PAIR=pair)
-        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=300)
-        outs.append(torch.load(path))
-    assert outs[0].keys() == outs[1].keys() and len(outs[0]) == 4
-    for k in outs[0]:
-        assert torch.equal(outs[0][k], outs[1][k]), k
-
-
-def test_shared_slab_forward_kernel_is_bit_identical_incl_training_stash():
-    """field_fwd3.cu (one weight stream per CTA shared by both tile slots, half-layer pipelining) performs the same MMAs in
-    the same K order and the same epilogue arithmetic as field_fwd.cu: raw output, point details and every byte of the
-    training stash must be equal -- inference and training mode, with / without bender, ragged and multi-wave sizes."""
-    from nonrigid_nerf_b200 import autograd as ag, ops, _lib
-    dev = _dev()
-    lib = _lib.load()
-    coarse, fine, bender, _ = helpers.build_models(O, 19, dev, True)
-    try:
-        for n, s in ((37, 64), (300, 128), (2500, 64), (5, 3)):
-            r = O.make_rays(19, n)
-            rays = helpers.rays8(r, dev)
-            z = ops.sample_coarse(rays, s, None, False)
-            for with_b in (True, False):
-                coarse.ray_bender = (bender if with_b else None,)
-                lat = r["latents"].to(dev) if with_b else None
-                got = {}
-                for kind in (1, 3):
-                    _lib.check(lib.nrn_select_forward_kernel(kind), "select")
-                    raw, det = ag.field_rays(coarse, rays, z, lat, True)
-                    stash = torch.zeros(lib.nrn_stash_bytes(n, s), dtype=torch.uint8, device=dev)
-                    nerf_pack = ops.pack_nerf(coarse)
-                    bender_pack = ops.pack_bender(bender) if with_b else None
-                    raw_t, det_t = ops.field_forward(rays, z, lat, nerf_pack, bender_pack, 5, None, None, None, True, stash)
-                    _lib.device_error_check()
-                    got[kind] = (raw, det, raw_t, det_t, stash)
-                a, b = got[1], got[3]
-                assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[0], a[2]), (n, s, with_b)
-                for k in a[1]:
-                    assert torch.equal(a[1][k], b[1][k]) and torch.equal(a[3][k], b[3][k]), (n, s, with_b, k)
-                n_tiles = (n * s + 127) // 128
-                used = n_tiles * 634880
-                assert torch.equal(a[4][:used], b[4][:used]), (n, s, with_b, "stash")
-    finally:
-        coarse.ray_bender = (bender,)
-        lib.nrn_select_forward_kernel(1)
-
-
-def test_shared_slab_dgrad_kernel_is_bit_identical_incl_gradient_stash():
-    """field_bwd3.cu vs field_bwd.cu through nrn_field_backward: the gradient stash (every dY image), hence the weight
-    gradients WGRAD derives from it, must be equal bit for bit; the per-ray latent gradient is accumulated with fp32 atomics
-    in both kernels (order-dependent): equal to rounding."""
-    import ctypes as C
-    from nonrigid_nerf_b200 import ops, _lib
-    dev = _dev()
-    lib = _lib.load()
-    coarse, fine, bender, _ = helpers.build_models(O, 23, dev, True)
-    try:
-        for n, s, with_b in ((37, 64, True), (700, 128, True), (2500, 64, True), (2500, 64, False), (5, 3, True)):
-            r = O.make_rays(23, n)
-            rays = helpers.rays8(r, dev)
-            z = ops.sample_coarse(rays, s, None, False)
-            lat = r["latents"].to(dev) if with_b else None
-            nerf_pack = ops.pack_nerf(coarse)
-            bender_pack = ops.pack_bender(bender) if with_b else None
-            stash = torch.zeros(lib.nrn_stash_bytes(n, s), dtype=torch.uint8, device=dev)
-            raw, det = ops.field_forward(rays, z, lat, nerf_pack, bender_pack, 5, None, None, None, True, stash)
-            g = torch.Generator().manual_seed(n)
-            d_raw = (torch.randn(n, s, 5, generator=g) * 1e-3).to(dev)
-            d_un = (torch.randn(n * s, 3, generator=g) * 1e-2).to(dev)
-            d_rg = (torch.randn(n * s, generator=g) * 1e-3).to(dev)
-            got = {}
-            for kind in (1, 3):
-                _lib.check(lib.nrn_select_backward_kernel(kind), "select")
-                a = _lib.NrnFieldBwdArgs()
-                a.n_rays, a.n_samples, a.out_ch = n, s, 5
-                a.d_raw, a.stash = d_raw.data_ptr(), stash.data_ptr()
-                gstash = torch.zeros(lib.nrn_grad_stash_bytes(n, s), dtype=torch.uint8, device=dev)
-                scratch = torch.empty(lib.nrn_wgrad_scratch_bytes(), dtype=torch.uint8, device=dev)
-                a.grad_stash, a.wgrad_scratch = gstash.data_ptr(), scratch.data_ptr()
-                a.nerf_packed = nerf_pack.data_ptr()
-                nerf_grad = torch.empty(lib.nrn_nerf_grad_floats(5), dtype=torch.float32, device=dev)
-                a.nerf_grad = nerf_grad.data_ptr()
-                bend_grad = d_lat = None
-                if with_b:
-                    a.bender_packed = bender_pack.data_ptr()
-                    a.unmasked_offsets, a.rigidity_mask = det["unmasked_offsets"].data_ptr(), det["rigidity_mask"].data_ptr()
-                    a.d_unmasked_offsets, a.d_rigidity_mask = d_un.data_ptr(), d_rg.data_ptr()
-                    bend_grad = torch.empty(lib.nrn_bender_grad_floats(), dtype=torch.float32, device=dev)
-                    d_lat = torch.empty(n, 32, dtype=torch.float32, device=dev)
-                    a.bender_grad, a.d_latents = bend_grad.data_ptr(), d_lat.data_ptr()
-                a.stream = torch.cuda.current_stream().cuda_stream
-                _lib.check(lib.nrn_field_backward(C.byref(a)), "field_backward")
-                _lib.device_error_check()
-                got[kind] = (gstash, nerf_grad, bend_grad, d_lat)
-            n_tiles = (n * s + 127) // 128
-            used = n_tiles * 618496
-            assert torch.equal(got[1][0][:used], got[3][0][:used]), (n, s, with_b, "gradient stash")
-            assert torch.equal(got[1][1], got[3][1]), (n, s, with_b, "nerf grad")
-            if with_b:
-                assert torch.equal(got[1][2], got[3][2]), (n, s, with_b, "bender grad")
-                torch.testing.assert_close(got[3][3], got[1][3], rtol=1e-4, atol=1e-9)
-    finally:
-        lib.nrn_select_backward_kernel(1)

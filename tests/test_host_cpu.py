@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert loaded.nrn_packed_nerf_bytes() > 2 * 990_000 and loaded.nrn_packed_bender_bytes() > 2 * 53_000
     assert loaded.nrn_nerf_grad_floats(5) == 527_237 - 32_896 and loaded.nrn_bender_grad_floats() == 16_193
     assert loaded.nrn_stash_bytes(1024, 64) == 512 * 634_880
-    assert loaded.nrn_stash_bytes(1, 7) == 4 * 634_880      # one ragged tile, rounded up to a group of four tiles
+    assert loaded.nrn_stash_bytes(1, 7) == 2 * 634_880      # one ragged tile, rounded up to a tile pair (two slots per CTA)
 
 
 def test_argument_validation_returns_error_codes_without_a_gpu():
