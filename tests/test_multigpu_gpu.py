@@ -38,6 +38,7 @@ def _build(dev, g):
     import types
     from nonrigid_nerf_b200 import optim
     seed, n = int(g["seed"]), int(g["n"])
+    torch.manual_seed(seed)      # the dead views_linears are default-initialised from the global generator: same on every rank
     coarse, fine, bender, _ = helpers.build_models(O, seed, dev)
     r = O.make_rays(seed, n)
     # per-ray random draws on the device, leading dimension = rays: RayShardedFunction shards them with their rays
