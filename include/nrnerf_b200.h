@@ -51,6 +51,8 @@ int nrn_pack_bender(const float* const* net_w /*5*/, const float* const* net_b /
  * c2w [3][4] row-major, intrinsics = (focal_x, focal_y, center_x, center_y); rays_o / rays_d [H*W][3] in the [H, W, 3]
  * order of the reference.  Bit-identical to the reference's float32 arithmetic. */
 int nrn_get_rays(const float* c2w, const float* intrinsics, int height, int width, float* rays_o, float* rays_d, void* stream);
+/* rays [n][8] = (o, d, near, far) as render() assembles them before batchify_rays (train.py:388-398), scalar near / far. */
+int nrn_pack_rays(const float* rays_o, const float* rays_d, float near, float far, int n_rays, float* rays, void* stream);
 /* A training batch computed on demand instead of gathered from the host table of every ray of every image
  * (train.py:1498-1517, :1546-1564): pix [n][3] int64 = (image, x, y) as in batch_pixel_indices; poses [n_images][3][4];
  * intrinsics [n_views][4]; image_to_view [n_images] int32 or NULL (single view); images [n_images][H][W][3] fp32 or NULL
@@ -214,20 +216,37 @@ typedef struct NrnRayLossArgs {
   const float* weights;            /* [n][S] coarse visibility weights (detached) or NULL */
   const float* unmasked_offsets;   /* [n][S][3] or NULL: no offsets term */
   const float* rigidity_mask;      /* [n][S] */
-  float lam_offsets;               /* offsets_loss_weight * (1/100)^(1 - global_step / N_iters) */
+  float lam_offsets;               /* offsets_loss_weight (times the schedule, unless sched_step is given) */
   float lam_rigidity;              /* rigidity_loss_weight */
   float* loss;                     /* out [n] */
   float* u_rgb; float* u_rgb0;     /* out [n][3]: d loss / d rgb, d loss / d rgb0 */
   float* u_unmasked_offsets;       /* out [n][S][3] */
   float* u_rigidity_mask;          /* out [n][S] */
   void* stream;
-  const float* lam_offsets_scale;  /* NULL, or device scalar multiplied into lam_offsets at run time: the regulariser
-                                      schedule (1/100)^(1 - global_step / N_iters) of train.py:229 as a device value, so
-                                      that a captured CUDA graph follows the schedule */
+  /* Regulariser schedule (1/100)^(1 - global_step / N_iters) of train.py:229 / :281 evaluated on the device: sched_step is a
+   * device scalar holding global_step (NULL: the caller folded the schedule into the weights), so that a captured CUDA graph
+   * follows the schedule.  divergence [n] (or NULL) is the per-ray divergence regulariser (nrn_divergence_forward), added as
+   * lam_divergence * schedule * divergence; u_divergence [n] receives d loss / d divergence. */
+  const float* sched_step;
+  float sched_n_iters;
+  const float* divergence;
+  float lam_divergence;
+  float* u_divergence;
 } NrnRayLossArgs;
 int nrn_ray_loss(const NrnRayLossArgs* args);
-/* out[i] = g[i / per_row] * unit[i]  (backward of nrn_ray_loss) */
+/* out[i] = g[i / per_row] * unit[i] */
 int nrn_scale_rows(const float* g, const float* unit, float* out, int64_t n, int per_row, void* stream);
+/* Backward of nrn_ray_loss in ONE launch: every out_k[i] = g[ray of i] * unit_k[i] for the (up to five) unit-gradient arrays
+ * nrn_ray_loss wrote (NULL pairs are skipped): rgb [n][3], rgb0 [n][3], unmasked_offsets [n][S][3], rigidity_mask [n][S],
+ * divergence [n]. */
+typedef struct NrnRayLossBwdArgs {
+  int32_t n_rays, n_samples;
+  const float* g;                  /* [n] upstream gradient of the per-ray loss */
+  const float* u_rgb; const float* u_rgb0; const float* u_unmasked_offsets; const float* u_rigidity_mask; const float* u_divergence;
+  float* d_rgb; float* d_rgb0; float* d_unmasked_offsets; float* d_rigidity_mask; float* d_divergence;
+  void* stream;
+} NrnRayLossBwdArgs;
+int nrn_ray_loss_backward(const NrnRayLossBwdArgs* args);
 
 /* ---- optimizer step: replaces torch.optim.Adam(params=grad_vars, lr, betas=(0.9, 0.999)) of train.py:656-658 and its
  * optimizer.step() at train.py:1608.  All trainable tensors live in one flat fp32 buffer (the host side makes the

@@ -69,7 +69,16 @@ class NrnRayLossArgs(C.Structure):
         ("lam_offsets", C.c_float), ("lam_rigidity", C.c_float),
         ("loss", _vp), ("u_rgb", _vp), ("u_rgb0", _vp), ("u_unmasked_offsets", _vp), ("u_rigidity_mask", _vp),
         ("stream", _vp),
-        ("lam_offsets_scale", _vp),
+        ("sched_step", _vp), ("sched_n_iters", C.c_float), ("divergence", _vp), ("lam_divergence", C.c_float), ("u_divergence", _vp),
+    ]
+
+
+class NrnRayLossBwdArgs(C.Structure):
+    _fields_ = [
+        ("n_rays", C.c_int32), ("n_samples", C.c_int32), ("g", _vp),
+        ("u_rgb", _vp), ("u_rgb0", _vp), ("u_unmasked_offsets", _vp), ("u_rigidity_mask", _vp), ("u_divergence", _vp),
+        ("d_rgb", _vp), ("d_rgb0", _vp), ("d_unmasked_offsets", _vp), ("d_rigidity_mask", _vp), ("d_divergence", _vp),
+        ("stream", _vp),
     ]
 
 
@@ -117,6 +126,7 @@ SYMBOLS = {
     "nrn_pack_bender": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.c_int, _vp, _vp]),
     "nrn_sample_coarse": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "nrn_get_rays": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "nrn_pack_rays": (C.c_int, [_vp, _vp, C.c_float, C.c_float, C.c_int, _vp, _vp]),
     "nrn_ray_batch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "nrn_median_visibility_index": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "nrn_field_forward": (C.c_int, [C.POINTER(NrnFieldArgs)]),
@@ -135,6 +145,7 @@ SYMBOLS = {
     "nrn_divergence_backward": (C.c_int, [C.POINTER(NrnDivArgs)]),
     "nrn_ray_loss": (C.c_int, [C.POINTER(NrnRayLossArgs)]),
     "nrn_scale_rows": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
+    "nrn_ray_loss_backward": (C.c_int, [C.POINTER(NrnRayLossBwdArgs)]),
     "nrn_adam_step": (C.c_int, [C.POINTER(NrnAdamArgs)]),
     "nrn_peer_window_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "nrn_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), C.c_char_p]),

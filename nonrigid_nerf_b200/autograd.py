@@ -375,10 +375,11 @@ def _flat_params_bender(bender):
 
 
 class _RayLossFn(torch.autograd.Function):
-    """Per-ray loss of training_wrapper_class.forward (train.py:208-242) in one kernel (csrc/loss.cu)."""
+    """Per-ray loss of training_wrapper_class.forward (train.py:208-287) in one kernel (csrc/loss.cu): data terms, offsets /
+    rigidity regulariser, and the (already reduced) divergence regulariser with its weight and the regularisers' schedule."""
 
     @staticmethod
-    def forward(ctx, rgb, rgb0, target, weights, unmasked, rigidity, lam_o, lam_r, lam_o_scale=None):
+    def forward(ctx, rgb, rgb0, target, weights, unmasked, rigidity, lam_o, lam_r, sched_step, sched_n_iters, div, lam_div):
         n = rgb.shape[0]
         dev = rgb.device
         lib = _lib.load()
@@ -387,7 +388,7 @@ class _RayLossFn(torch.autograd.Function):
         a.rgb, a.target = keep[0].data_ptr(), keep[1].data_ptr()
         u_rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
         a.u_rgb = u_rgb.data_ptr()
-        u_rgb0 = u_off = u_rig = None
+        u_rgb0 = u_off = u_rig = u_div = None
         if rgb0 is not None:
             keep.append(rgb0.detach().contiguous().float())
             a.rgb0 = keep[-1].data_ptr()
@@ -403,40 +404,51 @@ class _RayLossFn(torch.autograd.Function):
             a.u_unmasked_offsets, a.u_rigidity_mask = u_off.data_ptr(), u_rig.data_ptr()
         a.n_rays, a.n_samples = n, s
         a.lam_offsets, a.lam_rigidity = float(lam_o), float(lam_r)
-        if lam_o_scale is not None:
-            keep.append(lam_o_scale.detach().float().contiguous())
-            a.lam_offsets_scale = keep[-1].data_ptr()
+        if sched_step is not None:
+            keep.append(sched_step.detach().float().contiguous())
+            a.sched_step, a.sched_n_iters = keep[-1].data_ptr(), float(sched_n_iters)
+        if div is not None:
+            keep.append(div.detach().contiguous().float())
+            u_div = torch.empty(n, dtype=torch.float32, device=dev)
+            a.divergence, a.lam_divergence, a.u_divergence = keep[-1].data_ptr(), float(lam_div), u_div.data_ptr()
         loss = torch.empty(n, dtype=torch.float32, device=dev)
         a.loss = loss.data_ptr()
         a.stream = torch.cuda.current_stream().cuda_stream
         with torch.cuda.device(dev):
             _lib.check(lib.nrn_ray_loss(C.byref(a)), "ray_loss")
-        ctx.units = (u_rgb, u_rgb0, u_off, u_rig)
+        ctx.units = (u_rgb, u_rgb0, u_off, u_rig, u_div)
+        ctx.ns = (n, s)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
         g = g.contiguous().float()
-        outs = []
-        for u in ctx.units:
-            if u is None:
-                outs.append(None)
-                continue
-            o = torch.empty_like(u)
-            with torch.cuda.device(u.device):
-                _lib.check(lib.nrn_scale_rows(C.c_void_p(g.data_ptr()), C.c_void_p(u.data_ptr()), C.c_void_p(o.data_ptr()), u.numel(),
-                                              u.numel() // g.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "scale_rows")
-            outs.append(o)
-        d_rgb, d_rgb0, d_off, d_rig = outs
-        return d_rgb, d_rgb0, None, None, d_off, d_rig, None, None, None
+        a = _lib.NrnRayLossBwdArgs()
+        a.n_rays, a.n_samples = ctx.ns
+        a.g = g.data_ptr()
+        outs = [None if u is None else torch.empty_like(u) for u in ctx.units]
+        names = ("rgb", "rgb0", "unmasked_offsets", "rigidity_mask", "divergence")
+        for nm, u, o in zip(names, ctx.units, outs):
+            if u is not None:
+                setattr(a, "u_" + nm, u.data_ptr())
+                setattr(a, "d_" + nm, o.data_ptr())
+        a.stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(g.device):
+            _lib.check(lib.nrn_ray_loss_backward(C.byref(a)), "ray_loss_backward")
+        d_rgb, d_rgb0, d_off, d_rig, d_div = outs
+        return d_rgb, d_rgb0, None, None, d_off, d_rig, None, None, None, None, d_div, None
 
 
 def ray_loss(rgb, rgb0, target, weights=None, unmasked=None, rigidity=None, lam_offsets=0.0, lam_rigidity=0.0,
-             lam_offsets_scale: Optional[torch.Tensor] = None):
-    """loss[N] = img2mse(rgb) + img2mse(rgb0) + lam_offsets * (offsets + lam_rigidity * rigidity regulariser).
-    `lam_offsets_scale` (0-dim CUDA tensor) is multiplied into lam_offsets on the device (CUDA-graph-safe schedule)."""
-    return _RayLossFn.apply(rgb, rgb0, target, weights, unmasked, rigidity, lam_offsets, lam_rigidity, lam_offsets_scale)
+             sched_step: Optional[torch.Tensor] = None, sched_n_iters: float = 1.0, divergence: Optional[torch.Tensor] = None,
+             lam_divergence: float = 0.0):
+    """loss[N] = img2mse(rgb) + img2mse(rgb0) + sched * lam_offsets * (offsets + lam_rigidity * rigidity regulariser)
+                 + sched * lam_divergence * divergence,   sched = (1/100)^(1 - sched_step / sched_n_iters) evaluated on the device
+    from the 0-dim CUDA tensor `sched_step` (CUDA-graph-safe), or 1 when sched_step is None (the caller folds the schedule
+    into the weights)."""
+    return _RayLossFn.apply(rgb, rgb0, target, weights, unmasked, rigidity, lam_offsets, lam_rigidity, sched_step, sched_n_iters,
+                            divergence, lam_divergence)
 
 
 class _CompositeFn(torch.autograd.Function):

@@ -166,6 +166,14 @@ int nrn_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, 
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "get_rays_kernel");
 }
 
+int nrn_pack_rays(const float* rays_o, const float* rays_d, float near, float far, int n_rays, float* rays, void* stream) {
+  if (n_rays < 0) return fail(NRN_E_INVALID, "nrn_pack_rays: bad size");
+  if (n_rays == 0) return NRN_OK;
+  if (!rays_o || !rays_d || !rays) return fail(NRN_E_INVALID, "nrn_pack_rays: null argument");
+  const cudaError_t e = nrn::launch_pack_rays(rays_o, rays_d, near, far, n_rays, rays, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "pack_rays_kernel");
+}
+
 int nrn_ray_batch(const int64_t* pix, int n, const float* poses, const float* K, const int32_t* image_to_view, const float* images,
                   int H, int W, float* rays_o, float* rays_d, float* target, void* stream) {
   if (n < 0 || H < 1 || W < 1) return fail(NRN_E_INVALID, "nrn_ray_batch: bad sizes");
@@ -411,13 +419,33 @@ int nrn_ray_loss(const NrnRayLossArgs* a) {
   if (!a->rgb || !a->target || !a->loss || !a->u_rgb || (a->rgb0 && !a->u_rgb0)) return fail(NRN_E_INVALID, "nrn_ray_loss: null argument");
   if (a->unmasked_offsets && (!a->weights || !a->rigidity_mask || !a->u_unmasked_offsets || !a->u_rigidity_mask))
     return fail(NRN_E_INVALID, "nrn_ray_loss: the offsets term needs weights, rigidity_mask and both gradient outputs");
+  if (a->divergence && !a->u_divergence) return fail(NRN_E_INVALID, "nrn_ray_loss: the divergence term needs u_divergence");
+  if (a->sched_step && !(a->sched_n_iters > 0.f)) return fail(NRN_E_INVALID, "nrn_ray_loss: sched_n_iters must be positive");
   nrn::RayLossParams p{};
   p.n = a->n_rays; p.S = a->n_samples;
   p.rgb = a->rgb; p.rgb0 = a->rgb0; p.target = a->target; p.w = a->weights; p.off = a->unmasked_offsets; p.rig = a->rigidity_mask;
-  p.lam_o = a->lam_offsets; p.lam_r = a->lam_rigidity; p.lam_o_scale = a->lam_offsets_scale;
+  p.lam_o = a->lam_offsets; p.lam_r = a->lam_rigidity;
+  p.sched_step = a->sched_step; p.sched_n_iters = a->sched_n_iters; p.div = a->divergence; p.lam_div = a->lam_divergence; p.u_div = a->u_divergence;
   p.loss = a->loss; p.u_rgb = a->u_rgb; p.u_rgb0 = a->u_rgb0; p.u_off = a->u_unmasked_offsets; p.u_rig = a->u_rigidity_mask;
   cudaError_t e = nrn::launch_ray_loss(p, static_cast<cudaStream_t>(a->stream));
   return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_loss_kernel");
+}
+
+int nrn_ray_loss_backward(const NrnRayLossBwdArgs* a) {
+  if (!a) return fail(NRN_E_INVALID, "nrn_ray_loss_backward: null args");
+  if (a->n_rays < 0 || a->n_samples < 1) return fail(NRN_E_INVALID, "nrn_ray_loss_backward: bad sizes");
+  if (a->n_rays == 0) return NRN_OK;
+  if (!a->g) return fail(NRN_E_INVALID, "nrn_ray_loss_backward: null upstream gradient");
+  nrn::RayLossBwdParams p{};
+  p.n = a->n_rays; p.S = a->n_samples; p.g = a->g;
+  const float* u[5] = {a->u_rgb, a->u_rgb0, a->u_unmasked_offsets, a->u_rigidity_mask, a->u_divergence};
+  float* d[5] = {a->d_rgb, a->d_rgb0, a->d_unmasked_offsets, a->d_rigidity_mask, a->d_divergence};
+  for (int k = 0; k < 5; ++k) {
+    if ((u[k] == nullptr) != (d[k] == nullptr)) return fail(NRN_E_INVALID, "nrn_ray_loss_backward: unit / output pair %d half given", k);
+    p.u[k] = u[k]; p.d[k] = d[k];
+  }
+  const cudaError_t e = nrn::launch_ray_loss_bwd(p, static_cast<cudaStream_t>(a->stream));
+  return e == cudaSuccess ? NRN_OK : cuda_fail(e, "ray_loss_bwd_kernel");
 }
 
 int nrn_scale_rows(const float* g, const float* unit, float* out, int64_t n, int per_row, void* stream) {

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_loss_kernel(const Ray
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * kWarpsPerBlock + warp;
   if (ray >= p.n) return;
+  // increasing schedule of the regularisers (train.py:229, :281), from the device-resident step counter when given
+  const float sched = p.sched_step ? powf(0.01f, 1.0f - __ldg(p.sched_step) / p.sched_n_iters) : 1.0f;
   float loss = 0.f;
   if (lane < 3) {
     const float t = p.target[ray * 3 + lane];
@@ -38,7 +40,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_loss_kernel(const Ray
     }
   }
   if (p.off) {
-    const float lam_o = p.lam_o_scale ? p.lam_o * __ldg(p.lam_o_scale) : p.lam_o;
+    const float lam_o = p.lam_o * sched;
     const float inv_s = 1.0f / static_cast<float>(p.S);
     float acc = 0.f;
     for (int i = lane; i < p.S; i += 32) {
@@ -64,7 +66,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ray_loss_kernel(const Ray
     loss += lam_o * acc * inv_s;
   }
   loss = warp_sum(loss);
-  if (lane == 0) p.loss[ray] = loss;
+  if (lane == 0) {
+    if (p.div) {
+      const float c = p.lam_div * sched;
+      loss += c * p.div[ray];
+      p.u_div[ray] = c;
+    }
+    p.loss[ray] = loss;
+  }
+}
+
+// out_k[i] = g[ray of i] * unit_k[i] for all unit arrays of the loss in one launch (grid-stride over the largest array)
+__global__ void ray_loss_bwd_kernel(const RayLossBwdParams p) {
+  const long long per[5] = {3, 3, 3ll * p.S, p.S, 1};
+  const long long total = static_cast<long long>(p.n) * per[2];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (p.u[k] && i < static_cast<long long>(p.n) * per[k]) p.d[k][i] = p.g[i / per[k]] * p.u[k][i];
+    }
+  }
 }
 
 // out[i] = g[i / per] * unit[i]
@@ -77,6 +98,14 @@ __global__ void ray_loss_scale_kernel(const float* __restrict__ g, const float* 
 cudaError_t launch_ray_loss(const RayLossParams& p, cudaStream_t st) {
   if (p.n <= 0) return cudaSuccess;
   ray_loss_kernel<<<(p.n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_ray_loss_bwd(const RayLossBwdParams& p, cudaStream_t st) {
+  if (p.n <= 0) return cudaSuccess;
+  const long long total = static_cast<long long>(p.n) * 3 * p.S;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  ray_loss_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(p);
   return cudaGetLastError();
 }
 cudaError_t launch_ray_loss_scale(const float* g, const float* unit, float* out, long long n, int per, cudaStream_t st) {

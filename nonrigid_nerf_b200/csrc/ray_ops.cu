@@ -398,6 +398,22 @@ __global__ void median_index_kernel(const float* __restrict__ w, int n, int S, l
   idx_out[ray] = arg;
 }
 
+// rays [n][8] = (o, d, near, far) from rays_o / rays_d [n][3] and scalar near / far (render, train.py:393-398: four small
+// PyTorch kernels and a concatenation there)
+__global__ void pack_rays_kernel(const float* __restrict__ o, const float* __restrict__ d, float near, float far, int n, float* __restrict__ rays) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* r = rays + static_cast<long long>(i) * 8;
+  r[0] = o[i * 3]; r[1] = o[i * 3 + 1]; r[2] = o[i * 3 + 2];
+  r[3] = d[i * 3]; r[4] = d[i * 3 + 1]; r[5] = d[i * 3 + 2];
+  r[6] = near; r[7] = far;
+}
+cudaError_t launch_pack_rays(const float* o, const float* d, float near, float far, int n, float* rays, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  pack_rays_kernel<<<(n + 255) / 256, 256, 0, st>>>(o, d, near, far, n, rays);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, float* rays_d, cudaStream_t st) {
   const long long total = static_cast<long long>(H) * W;
   if (total == 0) return cudaSuccess;

@@ -45,6 +45,7 @@ cudaError_t launch_composite_bwd(const CompositeBwdParams& p, cudaStream_t st);
 cudaError_t launch_get_rays(const float* c2w, const float* K, int H, int W, float* rays_o, float* rays_d, cudaStream_t st);
 cudaError_t launch_ray_batch(const long long* pix, int n, const float* poses, const float* K, const int* image_to_view,
                              const float* images, int H, int W, float* rays_o, float* rays_d, float* target, cudaStream_t st);
+cudaError_t launch_pack_rays(const float* o, const float* d, float near, float far, int n, float* rays, cudaStream_t st);
 cudaError_t launch_median_index(const float* w, int n, int S, long long* idx, cudaStream_t st);
 
 }  // namespace nrn

@@ -298,6 +298,16 @@ def intrinsics_row(intrin) -> list:
     return [float(intrin["focal_x"]), float(intrin["focal_y"]), float(intrin["center_x"]), float(intrin["center_y"])]
 
 
+def pack_rays(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float) -> torch.Tensor:
+    """[N, 8] = (o, d, near, far) for scalar near / far in one launch (train.py:388-398)."""
+    rays_o, rays_d = _f32c(rays_o, "rays_o"), _f32c(rays_d, "rays_d")
+    n = rays_o.shape[0]
+    rays = torch.empty(n, 8, dtype=torch.float32, device=rays_o.device)
+    with torch.cuda.device(rays_o.device):
+        _lib.check(_lib.load().nrn_pack_rays(_ptr(rays_o), _ptr(rays_d), float(near), float(far), n, _ptr(rays), _stream()), "pack_rays")
+    return rays
+
+
 def get_rays(c2w: torch.Tensor, intrin) -> Tuple[torch.Tensor, torch.Tensor]:
     """get_rays (run_nerf_helpers.py:588-605): rays_o, rays_d [H, W, 3] of one camera, computed on the device."""
     if not c2w.is_cuda:

@@ -276,32 +276,32 @@ class training_wrapper_class(torch.nn.Module):
         detailed = args.offsets_loss_weight > 0.0 or args.divergence_loss_weight > 0.0
         rgb, disp, acc, extras = T.render(rays_o, rays_d, chunk=args.chunk, verbose=i < 10, retraw=True,
                                           additional_pixel_information=info, detailed_output=detailed, **render_kwargs_train)
-        # increasing schedule of the regularisers (train.py:229, :281).  `global_step` may be a 0-dim CUDA tensor: the
-        # schedule is then evaluated on the device, so a step captured in a CUDA graph follows it when replayed.
+        # increasing schedule of the regularisers, (1/100)^(1 - global_step / N_iters) (train.py:229, :281).  `global_step` may be
+        # a 0-dim CUDA tensor: the schedule is then evaluated inside the loss kernel, so a step captured in a CUDA graph
+        # follows it when replayed.
         if isinstance(global_step, torch.Tensor):
-            sched = torch.pow(torch.full((), 0.01, dtype=torch.float32, device=dev), 1.0 - global_step.float() / float(args.N_iters))
-            lam_o, lam_o_scale = args.offsets_loss_weight, sched
+            sched, sched_step = 1.0, global_step
         else:
-            sched = (1.0 / 100.0) ** (1 - (global_step / args.N_iters))
-            lam_o, lam_o_scale = args.offsets_loss_weight * sched, None
+            sched, sched_step = (1.0 / 100.0) ** (1 - (global_step / args.N_iters)), None
         use_offsets = self.ray_bender is not None and args.offsets_loss_weight > 0.0
-        # data term (fine + coarse) and offsets / rigidity regulariser (train.py:208-242) in one fused kernel
-        loss = _ag.ray_loss(rgb, extras.get("rgb0"), target_s,
-                            extras["visibility_weights"] if use_offsets else None,
-                            extras["unmasked_offsets"] if use_offsets else None,
-                            extras["rigidity_mask"] if use_offsets else None,
-                            lam_o if use_offsets else 0.0, args.rigidity_loss_weight,
-                            lam_o_scale if use_offsets else None)
+        div = None
         if self.ray_bender is not None and args.divergence_loss_weight > 0.0:
-            # exact_divergence = False, backprop_into_weights = False (train.py:246-247); fused closed-form kernel
-            # weights 1 - exp(-relu(opacity_alpha)) (train.py:267) are formed inside the kernels
-            # Hutchinson probes: torch.randn like run_nerf_helpers.py:110, or injected with the other random draws
-            # (render_kwargs_train["randomness"]["e"], [N, N_samples, 3] or [N * N_samples, 3]) for exact reproduction
+            # exact_divergence = False, backprop_into_weights = False (train.py:246-247); fused closed-form kernels; the weights
+            # 1 - exp(-relu(opacity_alpha)) (train.py:267) are formed inside them.  Hutchinson probes: torch.randn like
+            # run_nerf_helpers.py:110, or injected with the other random draws (render_kwargs_train["randomness"]["e"],
+            # [N, N_samples, 3] or [N * N_samples, 3]) for exact reproduction
             rnd = render_kwargs_train.get("randomness")
             probes = rnd.get("e") if isinstance(rnd, dict) else None
             div = _ag.divergence_loss(extras["unmasked_offsets"], extras["rigidity_mask"], None, self.ray_bender,
                                       e=None if probes is None else probes.to(dev).reshape(-1, 3), opacity_alpha=extras["opacity_alpha"])
-            loss = loss + (args.divergence_loss_weight * sched) * div
+        # data term (fine + coarse), offsets / rigidity regulariser (train.py:208-242) and the weighted divergence term
+        # (train.py:278-286) in one fused kernel
+        loss = _ag.ray_loss(rgb, extras.get("rgb0"), target_s,
+                            extras["visibility_weights"] if use_offsets else None,
+                            extras["unmasked_offsets"] if use_offsets else None,
+                            extras["rigidity_mask"] if use_offsets else None,
+                            args.offsets_loss_weight * sched if use_offsets else 0.0, args.rigidity_loss_weight,
+                            sched_step, float(args.N_iters), div, args.divergence_loss_weight * sched)
         return loss
 
 

@@ -5,12 +5,14 @@ names, argument meaning, return structure and error behaviour (train.py:27-137, 
 :724-980), but run on the fused sm_100a kernels.  torch.nn.DataParallel (train.py:290-323) is
 replaced by ray sharding over torch.distributed/NCCL (parallel.py).
 
-Randomness is drawn host-side from the global torch generator in the reference's order
-(t_rand -> sigma noise coarse -> u -> sigma noise fine; train.py:861, :753, run_nerf_helpers.py:666)
-and passed to the kernels, so a seeded run consumes the same stream as the reference.
+Randomness (t_rand, sigma noise coarse, u, sigma noise fine; train.py:861, :753, run_nerf_helpers.py:666) comes from the
+global torch generator, but pooled: one torch.rand and one torch.randn per render_rays call, sliced into the four arrays --
+the same distributions, NOT the same values a seeded reference run would draw with its four calls.  Exact reproduction of
+a reference run goes through the `randomness=` keyword (the four tensors given explicitly).
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import autograd as _ag
@@ -200,9 +202,12 @@ def render(rays_o, rays_d, chunk=1024 * 32, ndc=True, near=0.0, far=1.0, use_vie
         raise RuntimeError("nonrigid_nerf_b200: rays must be CUDA tensors (there is no CPU path)")
     rays_o = torch.reshape(rays_o, [-1, 3]).float()
     rays_d = torch.reshape(rays_d, [-1, 3]).float()
-    near_t = near * torch.ones_like(rays_d[..., :1])
-    far_t = far * torch.ones_like(rays_d[..., :1])
-    rays = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+    if isinstance(near, torch.Tensor) or isinstance(far, torch.Tensor) or np.ndim(near) > 0 or np.ndim(far) > 0:
+        near_t = torch.as_tensor(near, dtype=torch.float32, device=rays_d.device) * torch.ones_like(rays_d[..., :1])
+        far_t = torch.as_tensor(far, dtype=torch.float32, device=rays_d.device) * torch.ones_like(rays_d[..., :1])
+        rays = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+    else:
+        rays = ops.pack_rays(rays_o, rays_d, float(near), float(far))     # scalar bounds (train.py:1463-1468): one launch
     all_ret = batchify_rays(rays, additional_pixel_information, chunk=chunk, detailed_output=detailed_output, **kwargs)
     for k in all_ret:
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))

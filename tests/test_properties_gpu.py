@@ -89,8 +89,9 @@ def test_less_common_switches_match_oracle(over):
         ret = O.render_rays(cp, fp, bp, r["rays_o"], r["rays_d"], r["near"], r["far"], r["latents"], kw["N_samples"], kw["N_importance"],
                             lindisp=kw["lindisp"], white_bkgd=kw["white_bkgd"])
     d = (rgb.cpu() - ret["rgb_map"]).abs().max().item()
-    assert d <= 5e-3, (over, d)
-    assert (acc.cpu() - ret["acc_map"]).abs().max().item() <= 5e-3
+    print(f"{over}: rgb L-inf {d:.3e}")
+    assert d <= 5e-4, (over, d)
+    assert (acc.cpu() - ret["acc_map"]).abs().max().item() <= 5e-4
     assert ex["raw"].shape == (n, kw["N_samples"] + kw["N_importance"], 5)
 
 

@@ -2,7 +2,7 @@
 oracle and against the golden vectors the executed reference produced.
 
 Tolerances (fp16 tensor-core operands, fp32 accumulation, vs the fp32 reference):
-  per-pixel RGB L-inf <= 5e-3, acc <= 5e-3, PSNR(new vs reference image) >= 50 dB
+  per-pixel RGB L-inf <= 5e-4, acc <= 5e-4 (measured 2-4e-6 at these weights), PSNR(new vs reference image) >= 50 dB
   gradients: relative L2 error per parameter tensor <= 6e-2 (fp16 activations and gradients with a
              dynamic loss scale; the error grows with depth of back-propagation, worst at layer 0)
 """
@@ -51,7 +51,7 @@ def test_render_matches_golden_caseB_and_keys():
     for name, ours in (("rgb_map", rgb), ("rgb0", extras["rgb0"]), ("acc_map", acc), ("acc0", extras["acc0"])):
         d = np.abs(ours.cpu().numpy() - g[name]).max()
         print(f"{name}: L-inf {d:.3e}")
-        assert d <= 5e-3, (name, d)
+        assert d <= 5e-4, (name, d)
     assert _psnr(rgb.cpu().numpy(), g["rgb_map"]) >= 50.0
     np.testing.assert_allclose(extras["z_std"].cpu().numpy(), g["z_std"], atol=2e-3)
     np.testing.assert_allclose(disp.cpu().numpy(), g["disp_map"], rtol=2e-2, atol=1e-3)
@@ -68,8 +68,8 @@ def test_render_golden_caseA_coarse_only_and_caseF_canonical():
     with torch.no_grad():
         rgb, disp, acc, extras = _render(coarse, None, bender, r, n_imp=0, detailed=False)
     assert set(str(k) for k in g["keys"]) == set(extras.keys())
-    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= 5e-3
-    assert np.abs(acc.cpu().numpy() - g["acc_map"]).max() <= 5e-3
+    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= 5e-4
+    assert np.abs(acc.cpu().numpy() - g["acc_map"]).max() <= 5e-4
     g = np.load(os.path.join(GOLD, "caseF_canonical.npz"))
     seed, n = int(g["seed"]), int(g["n"])
     coarse, fine, _, _ = helpers.build_models(O, seed, DEV, with_bender=False)
@@ -77,8 +77,8 @@ def test_render_golden_caseA_coarse_only_and_caseF_canonical():
     with torch.no_grad():
         rgb, disp, acc, extras = _render(coarse, fine, None, r)
     assert set(str(k) for k in g["keys"]) == set(extras.keys())
-    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= 5e-3
-    assert np.abs(extras["rgb0"].cpu().numpy() - g["rgb0"]).max() <= 5e-3
+    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= 5e-4
+    assert np.abs(extras["rgb0"].cpu().numpy() - g["rgb0"]).max() <= 5e-4
 
 
 def test_render_golden_caseD_test_time_knobs():
@@ -123,8 +123,8 @@ def test_training_step_forward_and_gradients_match_oracle_and_golden():
     for name, ours in (("rgb_map", rgb), ("rgb0", extras["rgb0"])):
         d = np.abs(ours.detach().cpu().numpy() - g[name]).max()
         print(f"{name}: L-inf {d:.3e}")
-        assert d <= 5e-3, (name, d)
-    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["loss"], atol=3e-3)
+        assert d <= 5e-4, (name, d)
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), g["loss"], atol=1e-3)
     # gradients vs the oracle's autograd on identical inputs
     cpo, fpo, bpo = O.clone_params(cp, True), O.clone_params(fp, True), O.clone_params(bp, True)
     lat_o = r["latents"].clone().requires_grad_(True)

@@ -291,3 +291,26 @@ def test_large_regulariser_weight_with_vanishing_data_term():
     e = _rel(lat.grad.cpu(), lat_o.grad)
     print(f"  latents: {e:.3e}")
     assert e <= 8e-2, e
+
+
+def test_device_scalar_schedule_equals_the_host_schedule():
+    """global_step as a 0-dim CUDA tensor (what a captured CUDA graph replays): the regularisers' schedule is evaluated inside
+    the loss kernel and must give the per-ray loss and gradients of the host-side float schedule (train.py:229, :281)."""
+    from nonrigid_nerf_b200 import _lib, parallel
+    g = np.load(os.path.join(GOLD, "caseH_training_wrapper.npz"))
+    seed, n = int(g["seed"]), int(g["n"])
+    out = {}
+    for mode in ("host", "device"):
+        coarse, fine, bender, _ = helpers.build_models(O, seed, DEV)
+        r = O.make_rays(seed, n)
+        rnd = dict(O.make_randomness(seed, n, 64, 64)); rnd["e"] = torch.from_numpy(g["e"])
+        latents = [torch.from_numpy(row.copy()).to(DEV).requires_grad_(True) for row in g["latent_table"]]
+        wrapper = parallel.training_wrapper_class(coarse, latents, fine_model=fine, ray_bender=bender)
+        step = int(g["global_step"]) if mode == "host" else torch.full((), float(g["global_step"]), device=DEV)
+        loss = wrapper(_targs(g), r["rays_o"].to(DEV), r["rays_d"].to(DEV), 100, _kwargs(coarse, fine, bender, r, rnd), r["target"].to(DEV),
+                       step, 0, {"imageid_to_timestepid": [int(v) for v in g["i2t"]]}, torch.from_numpy(g["pix"]).to(DEV))
+        loss.mean().backward()
+        _lib.device_error_check()
+        out[mode] = (loss.detach().cpu(), bender.network[0].weight.grad.cpu().clone(), torch.stack([l.grad for l in latents]).cpu())
+    for a, b in zip(out["host"], out["device"]):
+        assert _rel(b, a) <= 2e-5, _rel(b, a)
