@@ -349,7 +349,8 @@ def main():
         e0.record()
         for i in range(loop_steps):
             if e2e:
-                loss = step(upload(pinned[i % pool]))   # host -> device copy of this step's inputs (pinned memory)
+                # host -> device copy of this step's inputs from pinned memory (straight into the graph's input buffers)
+                loss = step(pinned[i % pool] if graphed is not None else upload(pinned[i % pool]))
                 loss.item()                              # device -> host read of the step's result
             else:
                 step(resident[i % pool])
@@ -424,7 +425,7 @@ def main():
         "roofline": roof,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed next to the N = 1 run only
         cb = cpu_baseline(N_RAND, 5, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores", "calibration_rays_per_s_by_threads") if k in cb}
     print(json.dumps(line), flush=True)

@@ -39,6 +39,8 @@ class GraphedStep:
             ops.FORCE_PACK = False
 
     def __call__(self, *inputs: torch.Tensor):
+        """Replay with new inputs (device tensors, or pinned host tensors: those are copied straight into the graph's input
+        buffers, one H2D copy each and no intermediate device tensor)."""
         for s, t in zip(self.static_inputs, inputs):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
