@@ -13,12 +13,14 @@ offsets / rigidity / divergence regularisers on, backward, Adam -- on synthetic 
   --workload render  BASELINE configs[2]: full-frame test-time forward 504 x 378, fixed pose, one latent per frame
   --workload sweep   BASELINE configs[4]: 1k-1M rays x {64,128,256} samples single pass, forward and forward+backward
 
-N > 1 (one process per GPU, torchrun): rays are sharded by rows; every rank's gradient arena lives in a CUDA-IPC window
-and the optimizer launch sums the ranks' arenas over NVLink while applying Adam (nonrigid_nerf_b200/csrc/peer.cu); the
-whole iteration -- forward, backward, reduce + Adam, loss gather -- is ONE CUDA graph per rank.  `--reducer nccl` selects
-the NCCL all-reduce over the same arena instead (collectives stay outside the graph).
+N > 1 (one process per GPU, torchrun): rays are sharded by rows; the gradients live in ONE flat arena per rank that is summed
+in place by one NCCL all-reduce per step (forward + backward replayed as a CUDA graph, collectives and Adam launched around
+it).  `--reducer peer` keeps the arena in a CUDA-IPC window instead and lets the optimizer launch sum the ranks' arenas over
+NVLink while applying Adam (nonrigid_nerf_b200/csrc/peer.cu): the whole iteration -- forward, backward, reduce + Adam, loss
+gather -- is then ONE CUDA graph per rank.
 """
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -30,6 +32,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+faulthandler.enable()      # a crash inside native code leaves a Python traceback on stderr
 
 METRIC = "rays/sec (64c+128f samples, 8x256 MLP), example_sequence training step"
 N_RAND = 1024
@@ -220,7 +223,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="train", choices=["train", "cfg4", "render", "sweep"])
     ap.add_argument("--n-rand", type=int, default=None, help="rays per GPU per step (train: 1024, cfg4: 8192)")
-    ap.add_argument("--reducer", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient reduction")
+    ap.add_argument("--reducer", default="nccl", choices=["peer", "nccl"],
+                    help="multi-GPU gradient reduction: nccl = in-place all-reduce over the gradient arena (default: the path exercised at every "
+                         "N); peer = sum over NVLink peer memory fused into the Adam launch, whole step in one CUDA graph (verified at N = 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-breakdown", action="store_true", help="skip the instrumented per-kernel pass")
