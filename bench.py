@@ -377,7 +377,10 @@ def main():
     # per-kernel breakdown: the same K steps once more with CUDA event records around every launch of this repo's
     # kernels (external event-record nodes inside the re-captured graph; they cost a few us per step themselves)
     per_step, ms_instrumented = {}, None
-    if not args.no_breakdown:
+    # (the instrumented re-capture is skipped with the peer reducer: its kernels spin on the other ranks' flags, and a second
+    # graph with event-record nodes in between is not something this bench needs -- the per-kernel breakdown is a per-GPU
+    # quantity, reported by the N = 1 and NCCL runs)
+    if not args.no_breakdown and peer_red is None:
         _lib.timing_enable(True)
         if graphed is not None:
             graphed = GraphedStep(local_step, resident[0], warmup=1)
