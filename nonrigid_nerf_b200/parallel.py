@@ -20,6 +20,7 @@ With world_size == 1 (or torch.distributed not initialised) the wrappers call st
 """
 from __future__ import annotations
 
+import weakref
 from typing import Any, Callable, List, Optional
 
 import torch
@@ -150,13 +151,16 @@ def all_reduce_gradients(params: List[torch.Tensor]) -> None:
 
 
 _HOOK_INSTALLED = False
-_SHARDED_PARAM_IDS: set = set()   # id() of every tensor a ray-sharded training function differentiates
+_SHARDED_PARAMS: dict = {}   # id(tensor) -> weak reference, for every tensor a ray-sharded training function differentiates
+                             # (the reference is checked: a recycled id() of a freed model can never enrol an unrelated optimizer)
 UNIFORM_GRADS = False   # True: a gradient that is None on one rank is None on all (skips the presence flags + host sync)
 
 
 def _register_sharded_params(params) -> None:
+    for k in [k for k, r in _SHARDED_PARAMS.items() if r() is None]:
+        del _SHARDED_PARAMS[k]
     for p in params:
-        _SHARDED_PARAM_IDS.add(id(p))
+        _SHARDED_PARAMS[id(p)] = weakref.ref(p)
 
 
 def _owns_sharded_params(optimizer) -> bool:
@@ -164,7 +168,8 @@ def _owns_sharded_params(optimizer) -> bool:
     all-reduce.  Any other optimizer in the process (a CPU baseline, a user's second model) is left alone."""
     for g in optimizer.param_groups:
         for p in g["params"]:
-            if id(p) in _SHARDED_PARAM_IDS:
+            ref = _SHARDED_PARAMS.get(id(p))
+            if ref is not None and ref() is p:
                 return True
     return False
 
