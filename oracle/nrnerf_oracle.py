@@ -60,6 +60,26 @@ def make_nerf_params(seed: int, out_ch: int = 5, density_boost: float = 1.0, inp
     return p
 
 
+def make_view_params(seed: int, density_boost: float = 1.0) -> Dict[str, Tensor]:
+    """The view-dependent branch of NeRF(use_viewdirs=True) (run_nerf_helpers.py:225-236): alpha_linear 256->1,
+    feature_linear 256->256, views_linears[0] (256 + 27)->128, rgb_linear 128->3; nn.Linear default init."""
+    rs = np.random.RandomState(seed)
+
+    def lin(out_f, in_f):
+        b = 1.0 / math.sqrt(in_f)
+        return (torch.from_numpy(rs.uniform(-b, b, size=(out_f, in_f)).astype(np.float32)),
+                torch.from_numpy(rs.uniform(-b, b, size=(out_f,)).astype(np.float32)))
+    p = {}
+    p["alpha_w"], p["alpha_b"] = lin(1, NERF_W)
+    p["feature_w"], p["feature_b"] = lin(NERF_W, NERF_W)
+    p["views_w"], p["views_b"] = lin(NERF_W // 2, NERF_W + 27)
+    p["rgb_w"], p["rgb_b"] = lin(3, NERF_W // 2)
+    if density_boost != 1.0:
+        p["alpha_w"] = p["alpha_w"] * density_boost
+        p["alpha_b"] = p["alpha_b"] * density_boost + 0.5 * density_boost
+    return p
+
+
 def make_bender_params(seed: int, latent: int = LATENT, offset_std: float = 0.01, rigid_std: float = 0.1) -> Dict[str, list]:
     """ray_bending init (run_nerf_helpers.py:433-505): kaiming-uniform(relu) hidden weights, zero
     hidden biases; the two zero-initialised output layers are re-drawn N(0, std) so that bending is
@@ -168,10 +188,44 @@ def nerf_mlp(npar: Dict[str, list], emb: Tensor) -> Tensor:
     return F.linear(h, npar["out_w"], npar["out_b"])
 
 
+def direction_encoding(d: Tensor) -> Tensor:
+    """embeddirs_fn = get_embedder(multires_views = 4) (train.py:582-586): [d, sin(2^k d), cos(2^k d)], k = 0..3 -> 27."""
+    return positional_encoding(d, 4)
+
+
+def viewdirs_via_finite_differences(bent: Tensor) -> Tensor:
+    """NeRF.viewdirs_via_finite_differences (run_nerf_helpers.py:316-356), difference_type = "backward": the direction of
+    sample i is the normalised step from sample i-1 to sample i of the BENT ray (sample 0 copies sample 1's), eps = 1e-6
+    added to the norm.  bent [N,S,3] -> [N*S, 27] (already encoded)."""
+    eps = 0.000001
+    diff = bent[:, 1:, :] - bent[:, :-1, :]
+    back = diff / (torch.norm(diff, dim=-1, keepdim=True) + eps)
+    dirs = torch.cat([back[:, 0, :].reshape(-1, 1, 3), back], dim=1)
+    return direction_encoding(dirs.reshape(-1, 3))
+
+
+def nerf_mlp_views(npar: Dict[str, list], vpar: Dict[str, Tensor], emb: Tensor, dirs_emb: Tensor) -> Tensor:
+    """NeRF.forward with use_viewdirs=True (run_nerf_helpers.py:272-304): trunk as nerf_mlp without its output layer, then
+    alpha = alpha_linear(h), feature = feature_linear(h), h = relu(views_linears[0](cat[feature, dirs])), rgb = rgb_linear(h);
+    output = cat[rgb, alpha] (4 channels)."""
+    h = emb
+    for i in range(NERF_D):
+        h = F.relu(F.linear(h, npar["pts_w"][i], npar["pts_b"][i]))
+        if i == NERF_SKIP:
+            h = torch.cat([emb, h], -1)
+    alpha = F.linear(h, vpar["alpha_w"], vpar["alpha_b"])
+    feature = F.linear(h, vpar["feature_w"], vpar["feature_b"])
+    hv = F.relu(F.linear(torch.cat([feature, dirs_emb], -1), vpar["views_w"], vpar["views_b"]))
+    rgb = F.linear(hv, vpar["rgb_w"], vpar["rgb_b"])
+    return torch.cat([rgb, alpha], -1)
+
+
 def query_field(npar, bp, pts: Tensor, latents: Tensor, rigidity_cutoff=None, scaling=None,
-                removal_threshold=None) -> Tuple[Tensor, Dict[str, Tensor]]:
+                removal_threshold=None, vpar=None, viewdirs: Optional[Tensor] = None) -> Tuple[Tensor, Dict[str, Tensor]]:
     """run_network + NeRF.forward for one pass (train.py:57-105, run_nerf_helpers.py:240-314).
-    pts [N,S,3], latents [N,Z] -> raw [N,S,C], details (each [N,S,k])."""
+    pts [N,S,3], latents [N,Z] -> raw [N,S,C], details (each [N,S,k]).
+    vpar (make_view_params) switches to the view-dependent head; with a bender the view directions are the finite differences
+    of the bent points (approx_nonrigid_viewdirs=True), without one the normalised ray directions `viewdirs` [N,3]."""
     n, s, _ = pts.shape
     flat = pts.reshape(-1, 3)
     details = {"initial_input_pts": flat.detach().clone()}
@@ -183,7 +237,14 @@ def query_field(npar, bp, pts: Tensor, latents: Tensor, rigidity_cutoff=None, sc
     else:
         bent = flat
     details["input_pts"] = bent.detach().clone()
-    raw = nerf_mlp(npar, positional_encoding(bent))
+    if vpar is not None:
+        if bp is not None:
+            dirs_emb = viewdirs_via_finite_differences(bent.reshape(n, s, 3))
+        else:
+            dirs_emb = direction_encoding(viewdirs[:, None, :].expand(n, s, 3).reshape(-1, 3))
+        raw = nerf_mlp_views(npar, vpar, positional_encoding(bent), dirs_emb)
+    else:
+        raw = nerf_mlp(npar, positional_encoding(bent))
     if removal_threshold is not None and bp is not None:
         kill = details["rigidity_mask"].flatten() >= removal_threshold
         raw = raw.clone()
@@ -258,16 +319,19 @@ def det_u(n: int, n_imp: int, device=None) -> Tensor:
 def render_rays(coarse, fine, bp, rays_o: Tensor, rays_d: Tensor, near, far, latents: Tensor,
                 s_c: int = 64, n_imp: int = 64, perturb: bool = False, raw_noise_std: float = 0.0,
                 rnd: Optional[Dict[str, Tensor]] = None, lindisp: bool = False, white_bkgd: bool = False,
-                rigidity_cutoff=None, scaling=None, removal_threshold=None, detailed: bool = True) -> Dict[str, Tensor]:
+                rigidity_cutoff=None, scaling=None, removal_threshold=None, detailed: bool = True,
+                vpar_c=None, vpar_f=None) -> Dict[str, Tensor]:
     """render_rays (train.py:792-980) with the coarse / importance-sample / fine assembly; keys as
-    in the reference's result dict."""
+    in the reference's result dict.  vpar_c / vpar_f (make_view_params): view-dependent heads (use_viewdirs=True,
+    train.py:364-381: viewdirs = rays_d / |rays_d|)."""
+    viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True) if vpar_c is not None else None
     n = rays_o.shape[0]
     # (device-agnostic: the training A/B of scripts/train_ab.py runs this restatement in fp32 on the GPU as the checker)
     near_t = torch.as_tensor(near, dtype=torch.float32, device=rays_o.device).expand(n).reshape(n, 1)
     far_t = torch.as_tensor(far, dtype=torch.float32, device=rays_o.device).expand(n).reshape(n, 1)
     z = stratified_z(near_t, far_t, s_c, rnd["t_rand"] if perturb else None, lindisp)
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z[:, :, None]
-    raw, det_c = query_field(coarse, bp, pts, latents, rigidity_cutoff, scaling, removal_threshold)
+    raw, det_c = query_field(coarse, bp, pts, latents, rigidity_cutoff, scaling, removal_threshold, vpar_c, viewdirs)
     noise_c = rnd["noise_c"] * raw_noise_std if raw_noise_std > 0 else None
     rgb, disp, acc, alpha, w, depth = raw2outputs(raw, z, rays_d, noise_c, white_bkgd)
     ret = {}
@@ -279,7 +343,7 @@ def render_rays(coarse, fine, bp, rays_o: Tensor, rays_d: Tensor, near, far, lat
         z_f, _ = torch.sort(torch.cat([z, z_samples], -1), -1)
         pts_f = rays_o[:, None, :] + rays_d[:, None, :] * z_f[:, :, None]
         raw, det_f = query_field(fine if fine is not None else coarse, bp, pts_f, latents, rigidity_cutoff, scaling,
-                                 removal_threshold)
+                                 removal_threshold, vpar_f if fine is not None else vpar_c, viewdirs)
         noise_f = rnd["noise_f"] * raw_noise_std if raw_noise_std > 0 else None
         rgb, disp, acc, alpha, w, depth = raw2outputs(raw, z_f, rays_d, noise_f, white_bkgd)
         ret.update({"rgb0": rgb0, "disp0": disp0, "acc0": acc0,

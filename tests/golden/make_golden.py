@@ -336,6 +336,60 @@ def main():
     np.savez_compressed(os.path.join(outdir, "caseJ_surface.npz"), seed=seed, n=n, rgb_map=np32(rgb), median_indices=median_indices.numpy(),
                         surface_pts=surface.astype(np.float32), surface_rigidity=rigidity.astype(np.float32),
                         fine_visibility_weights=np32(det["fine_visibility_weights"]))
+
+    # ---------------- case K: view-dependent head + approximate non-rigid view directions (row f1) -----------
+    # use_viewdirs=True, approx_nonrigid_viewdirs=True (run_nerf_helpers.py:233-236, 284-304, 316-356; train.py:364-381).
+    # Not implemented by the CUDA path yet (it raises): this case pins the ORACLE's restatement for the round that builds it.
+    seed, n = 900, 64
+    embed_fn, input_ch = rh.get_embedder(10, 0)
+    embeddirs_fn, input_ch_views = rh.get_embedder(4, 0)
+    bp = O.make_bender_params(seed + 2)
+    bender = rh.ray_bending(input_ch, 32, "simple_neural", embed_fn)
+    load_bender(bender, bp)
+    mods = []
+    for k, ns in ((0, 64), (1, 128)):
+        cp_k, vp_k = O.make_nerf_params(seed + k, 5, 30.0), O.make_view_params(seed + 10 + k, 30.0)
+        m = rh.NeRF(D=8, W=256, input_ch=input_ch, output_ch=5, skips=[4], input_ch_views=input_ch_views, use_viewdirs=True,
+                    ray_bender=bender, ray_bending_latent_size=32, embeddirs_fn=embeddirs_fn, num_ray_samples=ns,
+                    approx_nonrigid_viewdirs=True, time_conditioned_baseline=False)
+        with torch.no_grad():
+            for i in range(8):
+                m.pts_linears[i].weight.copy_(cp_k["pts_w"][i]); m.pts_linears[i].bias.copy_(cp_k["pts_b"][i])
+            m.alpha_linear.weight.copy_(vp_k["alpha_w"]); m.alpha_linear.bias.copy_(vp_k["alpha_b"])
+            m.feature_linear.weight.copy_(vp_k["feature_w"]); m.feature_linear.bias.copy_(vp_k["feature_b"])
+            m.views_linears[0].weight.copy_(vp_k["views_w"]); m.views_linears[0].bias.copy_(vp_k["views_b"])
+            m.rgb_linear.weight.copy_(vp_k["rgb_w"]); m.rgb_linear.bias.copy_(vp_k["rgb_b"])
+        mods.append(m)
+    coarse, fine = mods
+
+    def query_fn_views(inputs, viewdirs, additional_pixel_information, network_fn, detailed_output=False):
+        return rt.run_network(inputs, viewdirs, additional_pixel_information, network_fn, embed_fn=embed_fn,
+                              embeddirs_fn=embeddirs_fn, netchunk=64 * 128, detailed_output=detailed_output)
+
+    kwk = {"network_query_fn": query_fn_views, "perturb": 0.0, "N_importance": 64, "network_fine": fine, "N_samples": 64,
+           "network_fn": coarse, "ray_bender": bender, "white_bkgd": False, "raw_noise_std": 0.0, "ndc": False, "lindisp": False}
+    rays = O.make_rays(seed, n)
+    latents = rays["latents"].clone().requires_grad_(True)
+    rgb, disp, acc, extras = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, near=rays["near"], far=rays["far"], use_viewdirs=True,
+                                       additional_pixel_information={"ray_bending_latents": latents}, detailed_output=True,
+                                       retraw=True, **kwk)
+    loss = rh.img2mse(rgb, rays["target"], n) + rh.img2mse(extras["rgb0"], rays["target"], n)
+    loss.mean().backward()
+    named = [("coarse." + k, v) for k, v in coarse.named_parameters()] + [("fine." + k, v) for k, v in fine.named_parameters()] + \
+            [("bender." + k, v) for k, v in bender.named_parameters()]
+    save = dict(seed=seed, n=n, rgb_map=np32(rgb), rgb0=np32(extras["rgb0"]), acc_map=np32(acc), raw=np32(extras["raw"][:8]),
+                loss=np32(loss), latents_grad=np32(latents.grad))
+    save.update(grad_summary(named))
+    # static scene (no bender): the view direction is the normalised ray direction itself (train.py:364-381, 80-84)
+    for m in mods:
+        m.ray_bender = (None,)
+    kws = dict(kwk, ray_bender=None)
+    with torch.no_grad():
+        rgb_s, _, acc_s, extras_s = rt.render(rays["rays_o"], rays["rays_d"], chunk=32768, near=rays["near"], far=rays["far"],
+                                              use_viewdirs=True, additional_pixel_information={"ray_bending_latents": rays["latents"]},
+                                              retraw=True, **kws)
+    save.update(static_rgb_map=np32(rgb_s), static_rgb0=np32(extras_s["rgb0"]), static_raw=np32(extras_s["raw"][:8]))
+    np.savez_compressed(os.path.join(outdir, "caseK_viewdirs.npz"), **save)
     print("golden vectors written to", outdir)
 
 

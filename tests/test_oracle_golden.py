@@ -217,6 +217,42 @@ def test_caseJ_surface_selection():
     assert np.array_equal(idx2.numpy(), g["median_indices"])
 
 
+def test_caseK_view_dependent_head_and_finite_difference_viewdirs():
+    """Row f1's oracle: use_viewdirs=True with approx_nonrigid_viewdirs=True, against the executed reference."""
+    g = load("caseK_viewdirs.npz")
+    seed, n = int(g["seed"]), int(g["n"])
+    cp, fp, bp = models(seed)
+    vc, vf = O.make_view_params(seed + 10, 30.0), O.make_view_params(seed + 11, 30.0)
+    cp, fp, bp, vc, vf = (O.clone_params(q, True) for q in (cp, fp, bp, vc, vf))
+    r = O.make_rays(seed, n)
+    lat = r["latents"].clone().requires_grad_(True)
+    ret = O.render_rays(cp, fp, bp, r["rays_o"], r["rays_d"], r["near"], r["far"], lat, 64, 64, vpar_c=vc, vpar_f=vf)
+    for k in ("rgb_map", "acc_map", "rgb0"):
+        close(ret[k], g[k], 5e-6, name=k)
+    assert ret["raw"].shape[-1] == 4
+    close(ret["raw"][:8], g["raw"], 5e-5, name="raw")
+    loss = O.training_loss(ret, r["target"], 0.0, 0.0, 0.0)
+    close(loss, g["loss"], 1e-5, name="loss")
+    loss.mean().backward()
+    close(lat.grad, g["latents_grad"], 1e-7, 2e-3, name="latents_grad")
+    for net, p, v in (("coarse", cp, vc), ("fine", fp, vf)):
+        for nm, t in ((f"{net}.views_linears.0.weight", v["views_w"]), (f"{net}.feature_linear.weight", v["feature_w"]),
+                      (f"{net}.alpha_linear.weight", v["alpha_w"]), (f"{net}.rgb_linear.weight", v["rgb_w"]),
+                      (f"{net}.pts_linears.0.weight", p["pts_w"][0]), (f"{net}.pts_linears.7.weight", p["pts_w"][7])):
+            gr = t.grad.reshape(-1)
+            close(gr[torch.from_numpy(g[nm + ".idx"])], g[nm + ".val"], 1e-7, 2e-3, name=nm)
+            assert abs(float(gr.norm()) - float(g[nm + ".norm"][0])) <= 1e-3 * float(g[nm + ".norm"][0]) + 1e-9, nm
+        assert p["out_w"].grad is None       # output_linear is dead with use_viewdirs=True
+    with torch.no_grad():                # static scene: the view direction is the ray's own
+        st = O.render_rays(cp, fp, None, r["rays_o"], r["rays_d"], r["near"], r["far"], r["latents"], 64, 64, vpar_c=vc, vpar_f=vf)
+    close(st["rgb_map"], g["static_rgb_map"], 5e-6, name="static rgb")
+    close(st["rgb0"], g["static_rgb0"], 5e-6, name="static rgb0")
+    close(st["raw"][:8], g["static_raw"], 5e-5, name="static raw")
+    nm = "bender.network.0.weight"       # the view directions depend on the bent points: the bender sees that gradient too
+    gr = bp["net_w"][0].grad.reshape(-1)
+    close(gr[torch.from_numpy(g[nm + ".idx"])], g[nm + ".val"], 1e-7, 2e-3, name=nm)
+
+
 def test_flop_ledger():
     cp = O.make_nerf_params(0)
     bp = O.make_bender_params(0)
