@@ -25,10 +25,8 @@ from typing import Any, Callable, List, Optional
 
 import torch
 import torch.distributed as dist
-import torch.nn.functional as F
 
 from . import autograd as _ag
-from . import run_nerf_helpers as H
 from . import train as T
 
 

@@ -3,7 +3,6 @@ reference (tests/golden/make_golden.py).  CPU only."""
 import os
 
 import numpy as np
-import pytest
 import torch
 
 import oracle.nrnerf_oracle as O
