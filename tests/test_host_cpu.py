@@ -50,6 +50,67 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
         _lib.check(-1, "unit test")
 
 
+def test_every_entry_point_validates_before_touching_the_device():
+    """Bad sizes / null pointers come back as NRN_E_INVALID with a message, empty inputs as NRN_OK -- all without a GPU
+    (no CUDA call is made before validation)."""
+    from nonrigid_nerf_b200 import _lib
+    lib = _lib.load()
+    bad = {
+        "get_rays sizes": lambda: lib.nrn_get_rays(None, None, -1, 4, None, None, None),
+        "get_rays null": lambda: lib.nrn_get_rays(None, None, 4, 4, None, None, None),
+        "pack_rays size": lambda: lib.nrn_pack_rays(None, None, 0.0, 1.0, -3, None, None),
+        "pack_rays null": lambda: lib.nrn_pack_rays(None, None, 0.0, 1.0, 3, None, None),
+        "ray_batch sizes": lambda: lib.nrn_ray_batch(None, 4, None, None, None, None, 0, 8, None, None, None, None),
+        "ray_batch null": lambda: lib.nrn_ray_batch(None, 4, None, None, None, None, 8, 8, None, None, None, None),
+        "median sizes": lambda: lib.nrn_median_visibility_index(None, 4, 0, None, None),
+        "median null": lambda: lib.nrn_median_visibility_index(None, 4, 64, None, None),
+        "scale_rows sizes": lambda: lib.nrn_scale_rows(None, None, None, 4, 0, None),
+        "scale_rows null": lambda: lib.nrn_scale_rows(None, None, None, 4, 3, None),
+        "field_backward null": lambda: lib.nrn_field_backward(None),
+        "composite_backward null": lambda: lib.nrn_composite_backward(None),
+        "divergence_forward null": lambda: lib.nrn_divergence_forward(None),
+        "ray_loss null": lambda: lib.nrn_ray_loss(None),
+        "ray_loss_backward null": lambda: lib.nrn_ray_loss_backward(None),
+        "peer_alloc null": lambda: lib.nrn_peer_alloc(4096, None, None),
+        "peer_open null": lambda: lib.nrn_peer_open(None, None),
+        "peer_reduce_adam null": lambda: lib.nrn_peer_reduce_adam(None, None),
+        "peer_gather_rows null": lambda: lib.nrn_peer_gather_rows(None, None, 4, None, None),
+    }
+    for what, call in bad.items():
+        assert call() == -1, what
+        assert len(lib.nrn_last_error()) > 0, what
+    empty = {
+        "get_rays": lambda: lib.nrn_get_rays(None, None, 0, 4, None, None, None),
+        "pack_rays": lambda: lib.nrn_pack_rays(None, None, 0.0, 1.0, 0, None, None),
+        "ray_batch": lambda: lib.nrn_ray_batch(None, 0, None, None, None, None, 8, 8, None, None, None, None),
+        "median": lambda: lib.nrn_median_visibility_index(None, 0, 64, None, None),
+        "scale_rows": lambda: lib.nrn_scale_rows(None, None, None, 0, 3, None),
+        "sample_coarse": lambda: lib.nrn_sample_coarse(None, None, 0, 64, 0, None, None),
+        "peer_close": lambda: lib.nrn_peer_close(None),
+        "peer_free": lambda: lib.nrn_peer_free(None),
+    }
+    for what, call in empty.items():
+        assert call() == 0, what
+    # struct-level checks
+    rl = _lib.NrnRayLossArgs()
+    rl.n_rays, rl.n_samples = 4, 0
+    assert lib.nrn_ray_loss(ctypes.byref(rl)) == -1 and b"bad sizes" in lib.nrn_last_error()
+    rl.n_samples = 64
+    assert lib.nrn_ray_loss(ctypes.byref(rl)) == -1 and b"null argument" in lib.nrn_last_error()
+    rb = _lib.NrnRayLossBwdArgs()
+    rb.n_rays, rb.n_samples = 4, 64
+    assert lib.nrn_ray_loss_backward(ctypes.byref(rb)) == -1 and b"upstream" in lib.nrn_last_error()
+    ctx = _lib.NrnPeerCtx()
+    ctx.world, ctx.rank = 9, 0
+    assert lib.nrn_peer_reduce_adam(ctypes.byref(ctx), None) == -1 and b"at most" in lib.nrn_last_error()
+    ctx.world, ctx.rank = 2, 2
+    assert lib.nrn_peer_gather_rows(ctypes.byref(ctx), None, 4, None, None) == -1
+    # the window layout the Python side assumes (peer.py): 1 KB of flags, two slots, then the arena; 256-byte granules
+    assert lib.nrn_peer_window_bytes(0, 0) == 1024
+    assert lib.nrn_peer_window_bytes(100, 10) == 1024 + 2 * 256 + 512
+    assert lib.nrn_peer_window_bytes(-1, 10) == 0
+
+
 def test_state_dict_keys_match_the_reference_checkpoint_layout():
     from nonrigid_nerf_b200 import run_nerf_helpers as H
     embed_fn, ch = H.get_embedder(10, 0)
