@@ -243,6 +243,86 @@ def test_ray_sharded_function_matches_single_process(tmp_path, uniform):
     torch.testing.assert_close(got["w"], net[0].weight.detach(), rtol=1e-5, atol=1e-6)
 
 
+class _ArenaSGD(torch.optim.Optimizer):
+    """CPU stand-in for optim.Adam's multi-GPU contract: one flat gradient arena whose views are the .grad tensors,
+    `gradient_arena()`, `reduces_gradients_itself`, and a step() that lets the attached reducer sum the arena in place."""
+
+    def __init__(self, params, lr):
+        params = list(params)
+        super().__init__(params, {"lr": lr})
+        self._gflat = torch.zeros(sum(p.numel() for p in params))
+        self._reducer, self.grads_in_arena, o = None, True, 0
+        for p in params:
+            p.grad = self._gflat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+
+    @property
+    def reduces_gradients_itself(self):
+        return self._reducer is not None and self.grads_in_arena
+
+    def gradient_arena(self):
+        return self._gflat
+
+    def zero_grad(self, set_to_none=False):
+        self._gflat.zero_()
+
+    def step(self):
+        if self.reduces_gradients_itself:
+            assert self._reducer.step(self, None) is False      # the NCCL-style reducer leaves the update to the optimizer
+        for g in self.param_groups:
+            for p in g["params"]:
+                p.data.add_(p.grad, alpha=-g["lr"])
+
+
+def _arena_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from nonrigid_nerf_b200 import parallel as P
+    torch.manual_seed(0)
+    net = torch.nn.Linear(5, 3)
+    opt = _ArenaSGD(net.parameters(), lr=0.1)
+    P._register_sharded_params(list(net.parameters()))
+    P._install_optimizer_hook()
+    fn = P.RayShardedFunction(_ToyStep(net))
+    g = torch.Generator().manual_seed(11)
+    arenas = []
+    for it in range(2):
+        rays, lat, tgt = torch.randn(9, 3, generator=g), torch.randn(9, 2, generator=g), torch.randn(9, 3, generator=g)
+        opt.zero_grad()
+        fn(rays, {"lat": lat}, 1.0, tgt).mean().backward()
+        assert net.weight.grad.data_ptr() == opt.gradient_arena().data_ptr()      # autograd accumulated INTO the arena views
+        opt.step()
+        arenas.append(opt.gradient_arena().clone())
+    assert isinstance(opt._reducer, P.NcclArenaReducer)          # attached by the hook on the first step
+    if rank == 0:
+        torch.save({"arenas": arenas, "w": net.weight.detach().clone()}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_arena_is_reduced_exactly_once_per_step(tmp_path):
+    """The optimizer hook hands an arena optimizer its reducer on the first step and then stays out of the way: the arena
+    is summed across ranks ONCE (not by the hook and again by step()), from the very first iteration on."""
+    out = str(tmp_path / "arena.pt")
+    mp.spawn(_arena_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    net = torch.nn.Linear(5, 3)
+    step = _ToyStep(net)
+    g = torch.Generator().manual_seed(11)
+    for it in range(2):
+        rays, lat, tgt = torch.randn(9, 3, generator=g), torch.randn(9, 2, generator=g), torch.randn(9, 3, generator=g)
+        net.zero_grad()
+        step(rays, {"lat": lat}, 1.0, tgt).mean().backward()
+        full = torch.cat([net.weight.grad.reshape(-1), net.bias.grad.reshape(-1)])
+        torch.testing.assert_close(got["arenas"][it], full, rtol=1e-5, atol=1e-6)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(p.grad, alpha=-0.1)
+    torch.testing.assert_close(got["w"], net.weight.detach(), rtol=1e-5, atol=1e-6)
+
+
 def test_single_process_wrappers_call_straight_through():
     from nonrigid_nerf_b200 import parallel as P
     net = torch.nn.Linear(5, 3)
