@@ -332,7 +332,7 @@ def main():
 
     def step(batch):
         iteration[0] += 1
-        optimizer.set_lr(lrate * (0.1 ** (iteration[0] / (lrate_decay * 1000))))   # per-iteration decay of train.py:1611-1616
+        optimizer.set_lr(lrate * (0.1 ** (iteration[0] / (lrate_decay * 1000))))   # per-iteration decay of train.py:1631-1642
         out = graphed(*batch) if graphed is not None else local_step(*batch)
         if fused_collectives:
             return out

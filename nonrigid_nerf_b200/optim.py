@@ -1,5 +1,5 @@
 """Optimizer of the training step: a drop-in for `torch.optim.Adam(params=grad_vars, lr=..., betas=(0.9, 0.999))`
-(train.py:656-658; stepped at train.py:1608, learning rate rewritten per iteration at train.py:1611-1616).
+(train.py:656-658; stepped at train.py:1610, learning rate rewritten per iteration at train.py:1631-1642).
 
 Memory layout (all fp32, one allocation each, in the order the parameters were given):
   * parameters  -- every nn.Parameter becomes a view into ONE flat buffer (names, shapes, state_dict untouched)
@@ -171,7 +171,7 @@ class Adam(torch.optim.Optimizer):
 
     def set_lr(self, lr: float) -> None:
         """Push a new learning rate now (use between CUDA-graph replays; eager code can simply assign
-        param_groups[0]['lr'] like train.py:1614-1616)."""
+        param_groups[0]['lr'] like train.py:1641-1642)."""
         self.param_groups[0]["lr"] = float(lr)
         self._push_lr(float(lr))
 
